@@ -1,0 +1,157 @@
+"""Pin the CPU oracle (oracle/numpitron_oracle.py) to golden vectors produced by the
+UNMODIFIED reference (tests/golden/make_golden.py).  literal=True must be bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import numpitron_oracle as O
+
+TINY = dict(d_model=32, n_heads=4, n_layers=2, vocab=17, seq_len=16)
+
+
+def eq(a, b):
+    np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_linear(golden_layers):
+    G = golden_layers
+    eq(O.linear_forward(G["linear/x"], G["linear/w"], G["linear/b"]), G["linear/y"])
+    dx, dw, db = O.linear_backward(G["linear/x"], G["linear/w"], G["linear/dy"], True)
+    eq(dx, G["linear/dx"]); eq(dw, G["linear/dw"]); eq(db, G["linear/db"])
+    # fast path: same numbers to fp32 rounding
+    np.testing.assert_allclose(O.linear_forward(G["linear/x"], G["linear/w"], G["linear/b"], literal=False),
+                               G["linear/y"], rtol=1e-5, atol=1e-6)
+
+
+def test_relu_softmax(golden_layers):
+    G = golden_layers
+    eq(O.relu_forward(G["relu/x"]), G["relu/y"])
+    eq(O.relu_backward(G["relu/x"], G["relu/dy"]), G["relu/dx"])
+    eq(O.softmax(G["softmax/x"]), G["softmax/y"])
+    eq(O.softmax_backward_jacobian(G["softmax/y"], G["softmax/dy"]), G["softmax/dx"])
+    np.testing.assert_allclose(O.softmax_backward_compact(G["softmax/y"], G["softmax/dy"]),
+                               G["softmax/dx"], rtol=1e-5, atol=1e-7)
+
+
+def test_layernorm(golden_layers):
+    G = golden_layers
+    y, ctx = O.layernorm_forward(G["ln/x"], G["ln/w"], G["ln/b"])
+    eq(y, G["ln/y"])
+    dx, dw, db = O.layernorm_backward(ctx, G["ln/w"], G["ln/dy"])
+    eq(dx, G["ln/dx"]); eq(dw, G["ln/dw"]); eq(db, G["ln/db"])
+
+
+def test_mlp(golden_layers):
+    G = golden_layers
+    a = O.linear_forward(G["mlp/x"], G["mlp/w1"], G["mlp/b1"])
+    r = O.relu_forward(a)
+    eq(O.linear_forward(r, G["mlp/w2"], G["mlp/b2"]), G["mlp/y"])
+    dr, dw2, db2 = O.linear_backward(r, G["mlp/w2"], G["mlp/dy"], True)
+    da = O.relu_backward(a, dr)
+    dx, dw1, db1 = O.linear_backward(G["mlp/x"], G["mlp/w1"], da, True)
+    eq(dx, G["mlp/dx"]); eq(dw1, G["mlp/dw1"]); eq(db1, G["mlp/db1"]); eq(dw2, G["mlp/dw2"]); eq(db2, G["mlp/db2"])
+
+
+@pytest.mark.parametrize("literal", [True, False])
+def test_attention(golden_layers, literal):
+    G = golden_layers
+    y, ctx = O.attention_forward(G["att/x"], G["att/wqkv"], G["att/wout"], 4, literal)
+    dx, dwqkv, dwout = O.attention_backward(ctx, G["att/wqkv"], G["att/wout"], G["att/dy"], literal)
+    if literal:
+        eq(y, G["att/y"]); eq(ctx["p"], G["att/p"]); eq(dx, G["att/dx"]); eq(dwqkv, G["att/dwqkv"]); eq(dwout, G["att/dwout"])
+    else:
+        for got, want in ((y, "att/y"), (dx, "att/dx"), (dwqkv, "att/dwqkv"), (dwout, "att/dwout")):
+            w = G[want]
+            np.testing.assert_allclose(got, w, rtol=1e-5, atol=1e-5 * np.abs(w).max())
+
+
+def test_embedding_quirks(golden_layers):
+    G = golden_layers
+    lo, hi = O.vocab_chunk_bounds(17, 1, 0)
+    assert (lo, hi) == (0, 16)  # Q7: token 16 is out of chunk at tp=1
+    y, ctx = O.embedding_forward(G["emb/tokens"].copy(), G["emb/E"], lo, hi, True)
+    eq(y, G["emb/y"])
+    assert not y[0, :3].any()
+    eq(O.positional_table(32, 16), G["emb/pos"])
+    eq(G["emb/pos"][:16] + y, G["emb/y_pos"])
+    eq(O.output_embedding_forward(G["emb/out_x"], G["emb/E"]), G["emb/logits"])
+    dx, dE = O.output_embedding_backward(G["emb/out_x"], G["emb/E"], G["emb/dlogits"])
+    eq(dx, G["emb/out_dx"]); eq(dE, G["emb/dE_gemm"])
+    eq(O.embedding_backward(ctx, dE.copy(), G["emb/dy"]), G["emb/dE"])
+    # chunk bounds for tp>1 agree with np.array_split whenever vocab % tp == 1 (Q8)
+    for v, tp in ((65, 2), (65, 4), (65, 8), (50257, 8), (17, 2)):
+        sizes = [a.shape[0] for a in np.array_split(np.arange(v), tp)]
+        for r in range(tp):
+            lo, hi = O.vocab_chunk_bounds(v, tp, r)
+            assert hi - lo == sizes[r] and lo == sum(sizes[:r])
+
+
+def test_loss(golden_layers):
+    G = golden_layers
+    loss, grads = O.softmax_cross_entropy_world([G["loss/logits"]], G["loss/labels"].copy(), [(0, 16)])
+    eq(loss, G["loss/loss"]); eq(grads[0], G["loss/dlogits"])
+
+
+def test_adam(golden_layers):
+    G = golden_layers
+    p, m, v = G["adam/p0"], np.zeros((8, 8), np.float32), np.zeros((8, 8), np.float32)
+    for i in range(3):
+        p, m, v = O.adam_update(p, G[f"adam/g{i}"], m, v, 1e-3, 0.9, 0.99)
+        eq(p, G[f"adam/p{i + 1}"])
+    eq(m, G["adam/m"]); eq(v, G["adam/v"])
+    assert p.dtype == np.float32
+
+
+def _tiny_batches(G, n=3):
+    return [(G[f"tiny/x{i}"], G[f"tiny/y{i}"]) for i in range(n)]
+
+
+def test_tiny_transformer_bit_exact(golden_layers):
+    G = golden_layers
+    t = O.OracleTransformer(**TINY, rng=np.random.default_rng(42), literal=True)
+    for i, (x, y) in enumerate(_tiny_batches(G)):
+        tr = {}
+        res = t.forward_loss(x, y)  # loss before the update
+        eq(res[0][0], G[f"tiny/loss{i}"])
+        t.train_step(x, y, tr)
+        if i == 0:
+            eq(tr["logits"][0], G["tiny/logits0"]); eq(tr["d_logits"][0], G["tiny/dlogits0"])
+            eq(tr["grads"]["embedding"], G["tiny/dE0"])
+            eq(tr["grads"]["block_1.qkv.weight"], G["tiny/dwqkv0_block1"])
+            eq(tr["grads"]["block_1.col.weight"], G["tiny/dw1_0_block1"])
+            eq(tr["grads"]["block_1.norm2.weight"], G["tiny/dn2w0_block1"])
+    eq(t.ranks[0][0].params["embedding"], G["tiny/E_final"])
+    eq(t.ranks[0][0].params["block_1.qkv.weight"], G["tiny/wqkv_final_block1"])
+
+
+def test_tiny_transformer_fast_mode(golden_layers):
+    G = golden_layers
+    t = O.OracleTransformer(**TINY, rng=np.random.default_rng(42), literal=False)
+    for i, (x, y) in enumerate(_tiny_batches(G)):
+        loss = t.train_step(x, y)[0]
+        np.testing.assert_allclose(loss, G[f"tiny/loss{i}"].mean(), rtol=2e-6)
+    np.testing.assert_allclose(t.ranks[0][0].params["embedding"], G["tiny/E_final"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("tp,dp", [(2, 1), (2, 2)])
+def test_tiny_world(golden_layers, tp, dp):
+    """The emulated tp x dp world against the reference run as tp*dp OS processes (gloo stand-in)."""
+    W = load_golden(f"tiny_tp{tp}_dp{dp}.npz")
+    t = O.OracleTransformer(**TINY, rng=np.random.default_rng(42), tp=tp, dp=dp, literal=True)
+    G = golden_layers
+    for i, (x, y) in enumerate(_tiny_batches(G)):
+        tr = {}
+        res = t.forward_loss(x, y)
+        for dr in range(dp):
+            for trk in range(tp):
+                np.testing.assert_allclose(res[dr][0], W[f"rank{dr * tp + trk}/loss{i}"], rtol=1e-6, atol=1e-6)
+        t.train_step(x, y, tr)
+    for dr in range(dp):
+        for trk in range(tp):
+            r = dr * tp + trk
+            np.testing.assert_allclose(t.ranks[dr][trk].params["embedding"], W[f"rank{r}/E_final"], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(t.ranks[dr][trk].params["block_0.col.weight"], W[f"rank{r}/w1_final_block0"],
+                                       rtol=1e-5, atol=1e-7)
+    if dp > 1:  # Q11: block weights diverge across DP replicas, the embedding does not
+        eq(t.ranks[0][0].params["embedding"], t.ranks[1][0].params["embedding"])
+        assert np.any(t.ranks[0][0].params["block_0.col.weight"] != t.ranks[1][0].params["block_0.col.weight"])
