@@ -1,0 +1,174 @@
+/*
+ * numpitron_b200 — C ABI of the B200 (sm_100a) kernels behind NuMPItron's layer API.
+ *
+ * The reference (lweitkamp/numpitron) is pure Python/NumPy and has no FFI of its own
+ * (SURVEY.md §8b); the boundary these entry points sit behind is the body of each layer's
+ * forward/backward/step.  Every declaration cites the reference expression(s) it replaces
+ * (paths relative to /root/reference/src/numpitron/).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; npt_last_error() gives the text;
+ *   - every data pointer is a DEVICE pointer owned by the caller; nothing is allocated or
+ *     freed behind the caller's back (scratch is passed in as workspace pointer + size);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs;
+ *   - matrices are row-major with explicit leading dimensions counted in ELEMENTS;
+ *   - fp32 unless a name says bf16 (bf16 = __nv_bfloat16, 2 bytes); tokens/labels are uint16
+ *     exactly as the reference's memmap (data/loader.py:32).
+ */
+#ifndef NUMPITRON_B200_H
+#define NUMPITRON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------- */
+const char* npt_last_error(void);
+int npt_version(void);
+/* Fills SM count and compute capability of the current device. */
+int npt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- dense contractions ---------------------------------------------------------------
+ * One strided-batched GEMM serves every contraction on the path:
+ *   Linear.forward   einsum("bsd,dh->bsh") + bias            nn/linear.py:44-47
+ *   Linear.backward  einsum("bsd,bsh->dh"), einsum("bsh,dh->bsd")   nn/linear.py:55,60
+ *   Attention        q@k^T, p@v and their backward products  nn/attention.py:47-52, 81-92
+ *   OutputEmbedding  x@E, einsum("bsd,bsv->dv"), d@E^T       nn/embedding.py:92,99,102
+ *
+ *   C[b] = alpha * op(A[b]) * op(B[b])   (+ bias[n])  (ReLU)  (* (mask[b] > 0))
+ * op(A) is M x K, op(B) is K x N.  trans_a = 0: A stored (M,K); 1: stored (K,M).
+ * trans_b = 0: B stored (K,N); 1: stored (N,K).
+ * Batch index i in [0, batch) maps to (i / batch_inner, i % batch_inner) and offsets
+ * X + outer*stride_X_outer + inner*stride_X_inner (elements) — this is how the per-head
+ * [q_h | k_h | v_h] column layout of the QKV projection (attention.py:43-45) is addressed
+ * without any transpose/copy.
+ */
+enum { NPT_GEMM_FP32_SIMT = 0,   /* fp32 FFMA, the fp32-accurate mode            */
+       NPT_GEMM_BF16_TC   = 1,   /* bf16 operands, tcgen05.mma + TMEM, fp32 accum */
+       NPT_GEMM_TF32X3_TC = 2 }; /* fp32 operands, 3xTF32 split on tcgen05       */
+
+typedef struct npt_gemm_args {
+  int32_t mode;            /* NPT_GEMM_* */
+  int32_t trans_a, trans_b;
+  int32_t M, N, K;
+  int32_t batch, batch_inner;          /* batch >= 1, batch_inner >= 1 */
+  const void* A; int64_t lda, stride_a_outer, stride_a_inner;  /* fp32 (mode 0,2) or bf16 (mode 1) */
+  const void* B; int64_t ldb, stride_b_outer, stride_b_inner;
+  float* C;        int64_t ldc,  stride_c_outer,  stride_c_inner;   /* fp32 out, may be NULL  */
+  void*  C_bf16;   int64_t ldcb, stride_cb_outer, stride_cb_inner;  /* bf16 out, may be NULL  */
+  float alpha;
+  const float* bias;       /* [N] or NULL; added after alpha                        */
+  int32_t relu;            /* 1: C = max(C, 0) after bias (MLP column linear, mlp.py:38-39) */
+  const void* mask;        /* NULL or tensor shaped like C: C *= (mask > 0)  (ReLU.backward, activation.py:42-43) */
+  int32_t mask_is_bf16;    /* dtype of mask */
+  int64_t ldmask, stride_mask_outer, stride_mask_inner;
+  void* workspace; size_t workspace_bytes;   /* split-K partials; see npt_gemm_workspace_bytes */
+} npt_gemm_args;
+
+size_t npt_gemm_workspace_bytes(const npt_gemm_args* args);
+int npt_gemm(const npt_gemm_args* args, void* stream);
+
+/* fp32 -> bf16 copy of a rows x cols matrix; columns [cols, ld_dst) of dst are zero-filled. */
+int npt_cast_f32_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst,
+                      int64_t rows, int64_t cols, void* stream);
+/* The hi/lo TF32 split used by NPT_GEMM_TF32X3_TC is done inside the GEMM kernel. */
+
+/* ---- LayerNorm — nn/normalization.py:22-52 ----------------------------------------------
+ * fwd: y = gamma*(x-mean)/sqrt(var+eps)+beta (+ residual: TransformerBlock.forward's
+ *      `norm(sub(x)) + x`, nn/transformer_block.py:20-21).  mean/var (population) are saved.
+ * bwd: dgamma = sum dy*xhat, dbeta = sum dy, dx = (g*dy - c1*xhat - c2) / sqrt(var)  — the
+ *      final division uses std WITHOUT eps exactly as normalization.py:45-50 does.
+ *      partial: workspace of npt_layernorm_bwd_workspace_bytes(rows,d) bytes.
+ */
+int npt_layernorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual,
+                      float* y, void* y_bf16, float* mean, float* var,
+                      int64_t rows, int32_t d, float eps, void* stream);
+size_t npt_layernorm_bwd_workspace_bytes(int64_t rows, int32_t d);
+int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, const float* var,
+                      const float* dy, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                      int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* ---- ReLU — nn/activation.py:38-43 (stand-alone; the GEMM epilogue fuses both) ---------- */
+int npt_relu_fwd(const float* x, float* y, void* y_bf16, int64_t n, void* stream);
+int npt_relu_bwd(const float* x, const float* dy, float* dx, void* dx_bf16, int64_t n, void* stream);
+
+/* Column sum over rows: db = dy.sum(axis=(0,1)) — nn/linear.py:57-58.  Deterministic two-stage. */
+size_t npt_colsum_workspace_bytes(int64_t rows, int32_t cols);
+int npt_colsum(const float* x, int64_t ld, float* out, int64_t rows, int32_t cols,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- causal softmax over attention scores — nn/attention.py:48-51,87; nn/activation.py:6-31
+ * fwd: P = softmax(where(j<=i, S/divisor, -inf)) row-wise over (rows_total = B*h*S) x S.
+ * bwd: dS = where(j<=i, P*(dP - sum_j dP*P), 0) / divisor   (compact form of the Jacobian).
+ */
+int npt_softmax_causal_fwd(const float* scores, float* p, void* p_bf16, int64_t n_mats, int32_t S,
+                           float divisor, void* stream);
+int npt_softmax_causal_bwd(const float* p, const float* dp, float* ds, void* ds_bf16,
+                           int64_t n_mats, int32_t S, float divisor, void* stream);
+
+/* ---- embeddings — nn/embedding.py:44-83,125-128 ---------------------------------------------
+ * gather: out[t,:] = (tok in [chunk_start,chunk_end) ? E[:, tok-chunk_start] : 0) (+ pos[t % S,:]).
+ *         E is (d, ldE>=V_local) row-major as the reference stores it.  `masked`=0 reproduces the
+ *         un-scattered path (no range mask).  pos may be NULL (added after the TP all-reduce).
+ * scatter_add: np.add.at(grad.T, tok[~mask], d_out[~mask]) in flattened (b,s) order, i.e. for
+ *         every vocab column the contributions are added one by one in increasing t, starting
+ *         from the value already in grad — bit-identical to NumPy.  No float atomics.
+ */
+int npt_embedding_gather(const uint16_t* tokens, const float* E, int64_t ldE, const float* pos,
+                         float* out, void* out_bf16, int64_t T, int32_t S, int32_t d,
+                         int32_t chunk_start, int32_t chunk_end, int32_t masked, void* stream);
+/* out[t,:] = pos[t % S,:] + x[t,:]  (PositionalEncoding.forward, embedding.py:125-128); out may alias x. */
+int npt_add_pos(const float* x, const float* pos, float* out, void* out_bf16, int64_t T, int32_t S, int32_t d, void* stream);
+size_t npt_embedding_scatter_add_workspace_bytes(int64_t T, int32_t V_local);
+int npt_embedding_scatter_add(const uint16_t* tokens, const float* d_out, float* grad, int64_t ldG,
+                              int64_t T, int32_t d, int32_t V_local, int32_t chunk_start,
+                              int32_t chunk_end, int32_t masked, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* ---- vocab-parallel softmax cross-entropy — nn/loss.py:6-50 -----------------------------------
+ * Split at the three TP all-reduces (loss.py:23-26, 34-35, 41-42):
+ *   stage1: rowmax[t] = max_v logits[t,v]                         -> all-reduce(max)
+ *   stage2: picked[t] = in-chunk ? logits[t,label]-rowmax : 0 ;  sumexp[t] = sum_v exp(logits-rowmax)
+ *                                                                  -> all-reduce(sum) x2
+ *   stage3: loss[t] = -picked + log(sumexp);  grad = exp(logits-rowmax)/sumexp - onehot*(in-chunk)
+ * `fused` does all three for tp == 1 in one pass.  The gradient is NOT divided by B*S (loss.py:47-48).
+ */
+int npt_softmax_ce_stage1(const float* logits, int64_t ld, float* rowmax, int64_t T, int32_t V_local, void* stream);
+int npt_softmax_ce_stage2(const float* logits, int64_t ld, const uint16_t* labels, const float* rowmax,
+                          float* picked, float* sumexp, int64_t T, int32_t V_local,
+                          int32_t chunk_start, int32_t chunk_end, void* stream);
+int npt_softmax_ce_stage3(const float* logits, int64_t ld, const uint16_t* labels, const float* rowmax,
+                          const float* picked, const float* sumexp, float* loss, float* grad,
+                          int64_t ldg, void* grad_bf16, int64_t ldgb, int64_t T, int32_t V_local,
+                          int32_t chunk_start, int32_t chunk_end, void* stream);
+int npt_softmax_ce_fused(const float* logits, int64_t ld, const uint16_t* labels, float* loss,
+                         float* grad, int64_t ldg, void* grad_bf16, int64_t ldgb, int64_t T,
+                         int32_t V_local, int32_t chunk_start, int32_t chunk_end, void* stream);
+/* mean of n floats into out[0] (train_step's `loss.mean()`, train_shakespeare.py:21); deterministic. */
+int npt_mean(const float* x, float* out, int64_t n, void* stream);
+
+/* ---- Adam — optimizer/adam.py:31-45 ----------------------------------------------------------------
+ * m = b1*m + omb1*g ; v = b2*v + omb2*g*g ; p -= (lr*(m/c1)) / (sqrt(v/c2) + eps)
+ * with the six scalars rounded to float32 by the caller exactly as NumPy's scalar promotion
+ * does (timestep never advances in the reference, so c1 = 1-beta1, c2 = 1-beta2).  Products and
+ * sums are individually rounded (no FMA contraction) so the update is bit-identical to NumPy.
+ * `tensors` is a device array of npt_adam_tensor; one launch updates all of them.
+ */
+typedef struct npt_adam_tensor {
+  float* p; const float* g; float* m; float* v;
+  void* p_bf16;            /* optional bf16 shadow of p refreshed in the same pass (may be NULL) */
+  int64_t n;               /* elements */
+  int64_t shadow_cols, shadow_ld;  /* if p_bf16: p is rows x shadow_cols, shadow row pitch shadow_ld */
+} npt_adam_tensor;
+int npt_adam_step(const npt_adam_tensor* tensors_dev, const npt_adam_tensor* tensors_host,
+                  int32_t n_tensors, float lr, float b1, float omb1, float b2, float omb2,
+                  float c1, float c2, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUMPITRON_B200_H */

@@ -1,0 +1,121 @@
+// npt_gemm: the one strided-batched GEMM entry point behind Linear / Attention / OutputEmbedding
+// (nn/linear.py:44-60, nn/attention.py:47-52,81-92, nn/embedding.py:92-102 of the reference).
+// Dispatches to the fp32 FFMA kernel (gemm_simt.cu) or the tcgen05 kernels (gemm_tc.cu) and
+// owns the deterministic split-K reduction.
+#include "gemm_common.cuh"
+
+namespace npt {
+
+GemmEpilogue make_epilogue(const npt_gemm_args& a) {
+  GemmEpilogue e;
+  e.C = a.C; e.ldc = a.ldc; e.sco = a.stride_c_outer; e.sci = a.stride_c_inner;
+  e.Cb = (__nv_bfloat16*)a.C_bf16; e.ldcb = a.ldcb; e.scbo = a.stride_cb_outer; e.scbi = a.stride_cb_inner;
+  e.alpha = a.alpha;
+  e.bias = a.bias;
+  e.relu = a.relu;
+  e.mask = a.mask; e.mask_bf16 = a.mask_is_bf16; e.ldm = a.ldmask; e.smo = a.stride_mask_outer; e.smi = a.stride_mask_inner;
+  e.M = a.M; e.N = a.N; e.batch_inner = a.batch_inner;
+  e.c_vec4 = a.C && aligned16(a.C) && a.ldc % 4 == 0 && a.stride_c_outer % 4 == 0 && a.stride_c_inner % 4 == 0;
+  e.cb_vec4 = a.C_bf16 && aligned8(a.C_bf16) && a.ldcb % 4 == 0 && a.stride_cb_outer % 4 == 0 && a.stride_cb_inner % 4 == 0;
+  if (a.mask) {
+    const bool al = a.mask_is_bf16 ? aligned8(a.mask) : aligned16(a.mask);
+    e.mask_vec4 = al && a.ldmask % 4 == 0 && a.stride_mask_outer % 4 == 0 && a.stride_mask_inner % 4 == 0;
+  } else {
+    e.mask_vec4 = 0;
+  }
+  e.bias_vec4 = a.bias && aligned16(a.bias);
+  return e;
+}
+
+// partial layout: [split][batch][M][N] fp32, contiguous.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, GemmEpilogue e, int splits, int batch) {
+  const int64_t mn = (int64_t)e.M * e.N;
+  const int64_t total4 = ((int64_t)batch * mn + 3) / 4;
+  const bool n4 = (e.N % 4) == 0;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (int64_t)gridDim.x * blockDim.x) {
+    if (n4) {
+      const int64_t i = q * 4;
+      const int b = (int)(i / mn);
+      const int64_t r = i - (int64_t)b * mn;
+      const int m = (int)(r / e.N), n = (int)(r - (int64_t)m * e.N);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < splits; ++s) {
+        const float4 p = *reinterpret_cast<const float4*>(partial + ((int64_t)s * batch) * mn + i);
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+      }
+      epi_store4(e, b, m, n, acc);
+    } else {
+      for (int k = 0; k < 4; ++k) {
+        const int64_t i = q * 4 + k;
+        if (i >= (int64_t)batch * mn) break;
+        const int b = (int)(i / mn);
+        const int64_t r = i - (int64_t)b * mn;
+        const int m = (int)(r / e.N), n = (int)(r - (int64_t)m * e.N);
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += partial[((int64_t)s * batch) * mn + i];
+        epi_store1(e, b, m, n, acc);
+      }
+    }
+  }
+}
+
+static int choose_splits(const npt_gemm_args& a) {
+  if (a.mode == NPT_GEMM_FP32_SIMT) return gemm_simt_splits(a);
+  return gemm_tc_splits(a);
+}
+
+}  // namespace npt
+
+using namespace npt;
+
+extern "C" {
+
+size_t npt_gemm_workspace_bytes(const npt_gemm_args* a) {
+  if (!a) return 0;
+  const int splits = choose_splits(*a);
+  if (splits <= 1) return 0;
+  return (size_t)splits * (size_t)a->batch * (size_t)a->M * (size_t)a->N * sizeof(float);
+}
+
+int npt_gemm(const npt_gemm_args* args, void* stream) {
+  NPT_REQUIRE(args != nullptr, "gemm: null args");
+  const npt_gemm_args& a = *args;
+  NPT_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+  NPT_REQUIRE(a.batch >= 1 && a.batch_inner >= 1, "gemm: bad batch %d/%d", a.batch, a.batch_inner);
+  NPT_REQUIRE(a.A && a.B, "gemm: null operand");
+  NPT_REQUIRE(a.C || a.C_bf16, "gemm: no output");
+  NPT_REQUIRE(a.lda >= (a.trans_a ? a.M : a.K), "gemm: lda too small");
+  NPT_REQUIRE(a.ldb >= (a.trans_b ? a.K : a.N), "gemm: ldb too small");
+  NPT_REQUIRE(!a.C || a.ldc >= a.N, "gemm: ldc too small");
+  NPT_REQUIRE(!a.C_bf16 || a.ldcb >= a.N, "gemm: ldcb too small");
+  NPT_REQUIRE(!a.mask || a.ldmask >= a.N, "gemm: ldmask too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a.mode != NPT_GEMM_FP32_SIMT) {
+    if (int rc = gemm_tc_supported(a)) return rc;
+  }
+  const GemmEpilogue epi = make_epilogue(a);
+  const int splits = choose_splits(a);
+  float* partial = nullptr;
+  if (splits > 1) {
+    const size_t need = (size_t)splits * a.batch * (size_t)a.M * a.N * sizeof(float);
+    NPT_REQUIRE(a.workspace && a.workspace_bytes >= need,
+                "gemm: split-K needs %zu workspace bytes, got %zu", need, a.workspace_bytes);
+    NPT_REQUIRE(aligned16(a.workspace), "gemm: workspace must be 16-byte aligned");
+    partial = (float*)a.workspace;
+  }
+  int rc = (a.mode == NPT_GEMM_FP32_SIMT) ? gemm_simt_launch(a, epi, splits, partial, st)
+                                          : gemm_tc_launch(a, epi, splits, partial, st);
+  if (rc) return rc;
+  if (splits > 1) {
+    const int64_t total4 = ((int64_t)a.batch * a.M * a.N + 3) / 4;
+    int64_t blocks = cdiv(total4, 256);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(partial, epi, splits, a.batch);
+    NPT_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // extern "C"

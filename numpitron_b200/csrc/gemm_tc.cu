@@ -1,0 +1,356 @@
+// bf16 tensor-core GEMM for sm_100a: TMA -> 128B-swizzled shared memory -> tcgen05.mma with the
+// fp32 accumulator in TMEM -> tcgen05.ld epilogue (alpha / bias / ReLU / ReLU-mask, fp32 and/or
+// bf16 stores).  Serves every dense contraction of the training step in the bf16 throughput mode
+// (nn/linear.py:44,55,60; nn/attention.py:48,52,81-92; nn/embedding.py:92,99,102).
+//
+// Layout support (no operand is ever transposed in memory):
+//   A K-major  (trans_a=0, stored M x K)   one TMA box {64 k, 128 m}
+//   A MN-major (trans_a=1, stored K x M)   two TMA boxes {64 m, 64 k}
+//   B K-major  (trans_b=1, stored N x K)   one TMA box {64 k, BN n}
+//   B MN-major (trans_b=0, stored K x N)   BN/64 TMA boxes {64 n, 64 k}
+// Batches ride in tensor-map dimensions 2 and 3 (inner / outer batch index), which is how the
+// per-head [q|k|v] column layout of the QKV projection is addressed in place.
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer (one elected lane),
+// warps 2-5 epilogue (one TMEM lane quarter each).  One 128 x BN output tile per CTA, two CTAs
+// per SM so one tile's epilogue overlaps the other's main loop.  Split-K partials go to a
+// workspace and are reduced in fixed order by gemm.cu (deterministic).
+#include <cuda.h>
+
+#include "gemm_common.cuh"
+
+namespace npt {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;  // bf16 elements = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 192;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): SWIZZLE_128B, version 1.
+//   K-major : LBO unused (1), SBO = 1024 B between 8-row groups.
+//   MN-major: LBO = bytes between 64-element MN chunks, SBO = 1024 B between 8-k groups.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M=128, N=BN.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4)                       // c_format = F32
+         | (1u << 7) | (1u << 10)        // a_format = b_format = BF16
+         | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
+         | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+               int K, int batch, int splits, int kb_per_split, GemmEpilogue epi, float* __restrict__ partial) {
+  using L = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bz = blockIdx.z;
+  const int b = bz / splits, split = bz - b * splits;
+  const int bo = b / epi.batch_inner, bi = b - bo * epi.batch_inner;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int kblocks = (K + TC_BK - 1) / TC_BK;
+  const int kb_begin = split * kb_per_split;
+  int kb_end = kb_begin + kb_per_split;
+  if (kb_end > kblocks) kb_end = kblocks;
+  const int nkb = kb_end - kb_begin;  // host guarantees nkb >= 1
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, it = i / STAGES;
+        mbar_wait(empty_bar + s, (it & 1) ^ 1);
+        mbar_expect_tx(full_bar + s, L::STAGE_BYTES);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        const int k0 = (kb_begin + i) * TC_BK;
+        if (A_MN) {
+          tma_load_4d(&tmA, full_bar + s, sa, m0, k0, bi, bo);
+          tma_load_4d(&tmA, full_bar + s, sa + 64 * TC_BK * 2, m0 + 64, k0, bi, bo);
+        } else {
+          tma_load_4d(&tmA, full_bar + s, sa, k0, m0, bi, bo);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_4d(&tmB, full_bar + s, sb + c * 64 * TC_BK * 2, n0 + c * 64, k0, bi, bo);
+        } else {
+          tma_load_4d(&tmB, full_bar + s, sb, k0, n0, bi, bo);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, it = i / STAGES;
+        mbar_wait(full_bar + s, it & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t sb = sa + L::A_BYTES;
+        // K-major: 16 k = 32 B inside the 128 B swizzle row.  MN-major: 16 k = two 8-k groups = 2048 B.
+        const uint64_t da = A_MN ? make_smem_desc(sa, 64 * TC_BK * 2, 1024) : make_smem_desc(sa, 16, 1024);
+        const uint64_t db = B_MN ? make_smem_desc(sb, 64 * TC_BK * 2, 1024) : make_smem_desc(sb, 16, 1024);
+        constexpr uint32_t adv_a = (A_MN ? 2048 : 32) >> 4, adv_b = (B_MN ? 2048 : 32) >> 4;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)
+          umma_bf16(tmem_base, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc, (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(empty_bar + s);  // frees this smem stage once the MMAs above retire
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    const int quarter = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int m = m0 + quarter * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      const int nb = n0 + c * 32;
+      if (m < M && nb < N) {
+        if (splits > 1) {
+          float* prow = partial + (((int64_t)split * batch + b) * M + m) * N;
+          if ((N & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (nb + j < N)
+                *reinterpret_cast<float4*>(prow + nb + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < N) prow[nb + j] = __uint_as_float(r[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            epi_store4(epi, b, m, nb + j, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 4-D bf16 tensor map: dims {inner (contiguous), rows, batch_inner, batch_outer}.
+static int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t ld, int64_t n_bi,
+                    int64_t s_bi, int64_t n_bo, int64_t s_bo, int box_inner, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  NPT_REQUIRE(enc != nullptr, "gemm(tc): cuTensorMapEncodeTiled not available from the driver");
+  const int64_t es = 2;
+  cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)n_bi, (cuuint64_t)n_bo};
+  const int64_t natural = ((rows * ld * es + 15) / 16) * 16;
+  cuuint64_t strides[3] = {(cuuint64_t)(ld * es), (cuuint64_t)(n_bi > 1 ? s_bi * es : natural),
+                           (cuuint64_t)(n_bo > 1 ? s_bo * es : natural)};
+  cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NPT_REQUIRE(r == CUDA_SUCCESS, "gemm(tc): cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld rows=%lld ld=%lld)",
+              (int)r, (long long)inner, (long long)rows, (long long)ld);
+  return 0;
+}
+
+int gemm_tc_supported(const npt_gemm_args& a) {
+  NPT_REQUIRE(a.mode == NPT_GEMM_BF16_TC, "gemm: mode %d is not implemented (use 0 = fp32 or 1 = bf16 tcgen05)", a.mode);
+  NPT_REQUIRE(aligned16(a.A) && aligned16(a.B), "gemm(tc): operand base pointers must be 16-byte aligned");
+  NPT_REQUIRE(a.lda % 8 == 0 && a.ldb % 8 == 0, "gemm(tc): bf16 leading dimensions must be multiples of 8 (lda=%lld ldb=%lld)",
+              (long long)a.lda, (long long)a.ldb);
+  NPT_REQUIRE(a.stride_a_outer % 8 == 0 && a.stride_a_inner % 8 == 0 && a.stride_b_outer % 8 == 0 && a.stride_b_inner % 8 == 0,
+              "gemm(tc): batch strides must be multiples of 8 elements");
+  return 0;
+}
+
+static int tc_bn(const npt_gemm_args& a) { return a.N <= 64 ? 64 : 128; }
+
+int gemm_tc_splits(const npt_gemm_args& a) {
+  const int bn = tc_bn(a);
+  const int64_t tiles = cdiv(a.M, TC_BM) * cdiv(a.N, bn) * a.batch;
+  const int64_t kblocks = cdiv(a.K, TC_BK);
+  const int64_t target = (int64_t)sm_count() * 2;
+  if (tiles >= target || kblocks < 8) return 1;
+  int64_t s = target / tiles;
+  if (s > kblocks / 4) s = kblocks / 4;  // >= 4 k-blocks (256 k) per split
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  const int64_t kps = cdiv(kblocks, s);
+  return (int)cdiv(kblocks, kps);  // no empty split
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, float* partial,
+                     const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
+  constexpr int STAGES = 3;
+  using L = TcSmem<BN, STAGES>;
+  auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int kblocks = (int)cdiv(a.K, TC_BK);
+  const int kps = (int)cdiv(kblocks, splits);
+  dim3 grid((unsigned)cdiv(a.N, BN), (unsigned)cdiv(a.M, TC_BM), (unsigned)(a.batch * splits));
+  kern<<<grid, TC_THREADS, L::TOTAL, st>>>(tmA, tmB, a.M, a.N, a.K, a.batch, splits, kps, epi, partial);
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, float* partial, cudaStream_t st) {
+  NPT_REQUIRE((int64_t)a.batch * splits <= 65535, "gemm(tc): batch*splits exceeds grid.z");
+  const int bn = tc_bn(a);
+  const int64_t n_bi = a.batch_inner, n_bo = cdiv(a.batch, a.batch_inner);
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (a.trans_a) rc = make_map(&tmA, a.A, a.M, a.K, a.lda, n_bi, a.stride_a_inner, n_bo, a.stride_a_outer, 64, 64);
+  else           rc = make_map(&tmA, a.A, a.K, a.M, a.lda, n_bi, a.stride_a_inner, n_bo, a.stride_a_outer, 64, TC_BM);
+  if (rc) return rc;
+  if (a.trans_b) rc = make_map(&tmB, a.B, a.K, a.N, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, bn);
+  else           rc = make_map(&tmB, a.B, a.N, a.K, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, 64);
+  if (rc) return rc;
+  const bool a_mn = a.trans_a != 0, b_mn = a.trans_b == 0;
+#define NPT_TC_CASE(BNV)                                                                          \
+  if (a_mn && b_mn) return launch_tc<BNV, true, true>(a, epi, splits, partial, tmA, tmB, st);     \
+  if (a_mn && !b_mn) return launch_tc<BNV, true, false>(a, epi, splits, partial, tmA, tmB, st);   \
+  if (!a_mn && b_mn) return launch_tc<BNV, false, true>(a, epi, splits, partial, tmA, tmB, st);   \
+  return launch_tc<BNV, false, false>(a, epi, splits, partial, tmA, tmB, st);
+  if (bn == 64) { NPT_TC_CASE(64) }
+  NPT_TC_CASE(128)
+#undef NPT_TC_CASE
+}
+
+}  // namespace npt

@@ -1,0 +1,349 @@
+// LayerNorm forward/backward — replaces nn/normalization.py:22-52 of the reference.
+//
+// HBM-bound row kernels: one warp owns one row, the row lives in registers (128-bit loads),
+// mean/variance are two-pass (the model's rows ride on a mean ~30-70x their std, SURVEY Q12,
+// so E[x^2]-E[x]^2 is not accurate enough), reductions are warp shuffles.
+// Algorithmic bytes: fwd 8 B/elem (+4 with residual, +2 with the bf16 shadow), bwd 12 B/elem.
+#include "common.cuh"
+
+namespace npt {
+
+constexpr int kLnWarps = 8;      // rows per block
+constexpr int kLnMaxVec = 8;     // float4 per lane -> d <= 1024 on the register path
+
+// ---------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ residual,
+                   float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
+                   float* __restrict__ mean_out, float* __restrict__ var_out,
+                   int64_t rows, int d, float eps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * kLnWarps + warp;
+  if (row >= rows) return;
+  const int nvec = d >> 2;  // float4 per row
+  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      v[i] = ld_stream(xr + c);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float mean = warp_sum(s) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+      q += (a * a + b * b) + (e * e + f * f);
+    }
+  }
+  const float var = warp_sum(q) / (float)d;
+  const float denom = sqrtf(var + eps);
+  if (lane == 0) {
+    mean_out[row] = mean;
+    var_out[row] = var;
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  const float4* r4 = residual ? reinterpret_cast<const float4*>(residual + row * d) : nullptr;
+  float4* yr = reinterpret_cast<float4*>(y + row * d);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+      float4 o;
+      // gamma * ((x - mean) / sqrt(var+eps)) + beta, each op rounded separately like NumPy.
+      o.x = __fadd_rn(__fmul_rn(g.x, __fdiv_rn(v[i].x - mean, denom)), b.x);
+      o.y = __fadd_rn(__fmul_rn(g.y, __fdiv_rn(v[i].y - mean, denom)), b.y);
+      o.z = __fadd_rn(__fmul_rn(g.z, __fdiv_rn(v[i].z - mean, denom)), b.z);
+      o.w = __fadd_rn(__fmul_rn(g.w, __fdiv_rn(v[i].w - mean, denom)), b.w);
+      if (r4) {
+        const float4 r = ld_stream(r4 + c);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      st_stream(yr + c, o);
+      if (yb) st_bf16x4(yb + row * d + (int64_t)c * 4, o);
+    }
+  }
+}
+
+// Any d: one block per row, three passes over the (L1/L2-resident) row.
+__global__ void __launch_bounds__(256)
+ln_fwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ residual,
+                    float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
+                    float* __restrict__ mean_out, float* __restrict__ var_out,
+                    int64_t rows, int d, float eps) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const float* xr = x + row * d;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) s += xr[c];
+  const float mean = block_sum(s, red) / (float)d;
+  float q = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float a = xr[c] - mean;
+    q += a * a;
+  }
+  const float var = block_sum(q, red) / (float)d;
+  const float denom = sqrtf(var + eps);
+  if (threadIdx.x == 0) {
+    mean_out[row] = mean;
+    var_out[row] = var;
+  }
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float o = __fadd_rn(__fmul_rn(gamma[c], __fdiv_rn(xr[c] - mean, denom)), beta[c]);
+    if (residual) o += residual[row * d + c];
+    y[row * d + c] = o;
+    if (yb) yb[row * d + c] = __float2bfloat16_rn(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Backward stage 1: dx per row + per-block partial dgamma/dbeta.
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                   const float* __restrict__ mean_in, const float* __restrict__ var_in,
+                   const float* __restrict__ dy, float* __restrict__ dx,
+                   __nv_bfloat16* __restrict__ dxb, float* __restrict__ partial,
+                   int64_t rows, int d, float eps) {
+  extern __shared__ float sm[];  // [kLnWarps][2][d]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = d >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4 g[NV], ag[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    g[i] = (c < nvec) ? __ldg(g4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_d = 1.0f / (float)d;
+  for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < rows;
+       row += (int64_t)gridDim.x * kLnWarps) {
+    const float mean = mean_in[row], var = var_in[row];
+    const float denom = sqrtf(var + eps);
+    const float stdv = sqrtf(var);  // inputs.std(): no eps (normalization.py:48-50)
+    const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+    const float4* dr = reinterpret_cast<const float4*>(dy + row * d);
+    float4 xh[NV], w[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        const float4 xv = ld_stream(xr + c), dv = ld_stream(dr + c);
+        xh[i].x = __fdiv_rn(xv.x - mean, denom); xh[i].y = __fdiv_rn(xv.y - mean, denom);
+        xh[i].z = __fdiv_rn(xv.z - mean, denom); xh[i].w = __fdiv_rn(xv.w - mean, denom);
+        w[i].x = g[i].x * dv.x; w[i].y = g[i].y * dv.y; w[i].z = g[i].z * dv.z; w[i].w = g[i].w * dv.w;
+        s1 += (xh[i].x * w[i].x + xh[i].y * w[i].y) + (xh[i].z * w[i].z + xh[i].w * w[i].w);
+        s2 += (w[i].x + w[i].y) + (w[i].z + w[i].w);
+        ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
+        ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+    float4* outr = reinterpret_cast<float4*>(dx + row * d);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        float4 o;
+        o.x = __fdiv_rn(w[i].x - c1 * xh[i].x - c2, stdv);
+        o.y = __fdiv_rn(w[i].y - c1 * xh[i].y - c2, stdv);
+        o.z = __fdiv_rn(w[i].z - c1 * xh[i].z - c2, stdv);
+        o.w = __fdiv_rn(w[i].w - c1 * xh[i].w - c2, stdv);
+        st_stream(outr + c, o);
+        if (dxb) st_bf16x4(dxb + row * d + (int64_t)c * 4, o);
+      }
+    }
+  }
+  // combine the block's warps: smem [warp][2][d]
+  float* mine = sm + (size_t)warp * 2 * d;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      reinterpret_cast<float4*>(mine)[c] = ag[i];
+      reinterpret_cast<float4*>(mine + d)[c] = ab[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < kLnWarps; ++w2) t += sm[(size_t)w2 * 2 * d + c];
+    partial[(size_t)blockIdx.x * 2 * d + c] = t;
+  }
+}
+
+// Any d: block per row-group, scalar loops.  partial layout identical.
+__global__ void __launch_bounds__(256)
+ln_bwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                    const float* __restrict__ mean_in, const float* __restrict__ var_in,
+                    const float* __restrict__ dy, float* __restrict__ dx,
+                    __nv_bfloat16* __restrict__ dxb, float* __restrict__ partial,
+                    int64_t rows, int d, float eps) {
+  __shared__ float red[32];
+  // per-thread column accumulators live in `partial` directly (each block owns its slice,
+  // each column is touched by exactly one thread of the block -> no race).
+  float* pg = partial + (size_t)blockIdx.x * 2 * d;
+  float* pb = pg + d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) { pg[c] = 0.f; pb[c] = 0.f; }
+  const float inv_d = 1.0f / (float)d;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float mean = mean_in[row], var = var_in[row];
+    const float denom = sqrtf(var + eps), stdv = sqrtf(var);
+    const float* xr = x + row * d;
+    const float* dr = dy + row * d;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      const float xh = __fdiv_rn(xr[c] - mean, denom), w = gamma[c] * dr[c];
+      s1 += xh * w;
+      s2 += w;
+      pg[c] += dr[c] * xh;
+      pb[c] += dr[c];
+    }
+    const float c1 = block_sum(s1, red) * inv_d;
+    const float c2 = block_sum(s2, red) * inv_d;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      const float xh = __fdiv_rn(xr[c] - mean, denom), w = gamma[c] * dr[c];
+      const float o = __fdiv_rn(w - c1 * xh - c2, stdv);
+      dx[row * d + c] = o;
+      if (dxb) dxb[row * d + c] = __float2bfloat16_rn(o);
+    }
+  }
+}
+
+// Stage 2: out[c] = sum_b partial[b][c]   (fixed order -> deterministic)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out0,
+                                       float* __restrict__ out1, int nblocks, int d) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * d) return;
+  float t = 0.f;
+  for (int b = 0; b < nblocks; ++b) t += partial[(size_t)b * 2 * d + c];
+  if (c < d) out0[c] = t; else out1[c - d] = t;
+}
+
+static int ln_bwd_blocks(int64_t rows) {
+  int64_t want = cdiv(rows, kLnWarps);
+  int64_t cap = (int64_t)sm_count() * 2;
+  return (int)(want < cap ? want : cap);
+}
+
+template <int NV>
+static int launch_fwd(const float* x, const float* g, const float* b, const float* r, float* y,
+                      void* yb, float* mean, float* var, int64_t rows, int d, float eps,
+                      cudaStream_t st) {
+  const int64_t grid = cdiv(rows, kLnWarps);
+  ln_fwd_warp_kernel<NV><<<(unsigned)grid, kLnWarps * 32, 0, st>>>(
+      x, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps);
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int NV>
+static int launch_bwd(const float* x, const float* g, const float* mean, const float* var,
+                      const float* dy, float* dx, void* dxb, float* partial, int nblocks,
+                      int64_t rows, int d, float eps, cudaStream_t st) {
+  const size_t smem = (size_t)kLnWarps * 2 * d * sizeof(float);
+  NPT_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_warp_kernel<NV>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ln_bwd_warp_kernel<NV><<<nblocks, kLnWarps * 32, smem, st>>>(
+      x, g, mean, var, dy, dx, (__nv_bfloat16*)dxb, partial, rows, d, eps);
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace npt
+
+using namespace npt;
+
+extern "C" {
+
+int npt_layernorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual,
+                      float* y, void* y_bf16, float* mean, float* var, int64_t rows, int32_t d,
+                      float eps, void* stream) {
+  NPT_REQUIRE(rows >= 0 && d > 0, "layernorm_fwd: bad shape rows=%lld d=%d", (long long)rows, d);
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (d % 4 == 0) && d <= kLnMaxVec * 128 && aligned16(x) && aligned16(y) &&
+                   aligned16(gamma) && aligned16(beta) && (!residual || aligned16(residual)) &&
+                   (!y_bf16 || aligned8(y_bf16));
+  if (vec) {
+    const int nv = (int)cdiv(d, 128);
+    switch (nv) {
+      case 1: return launch_fwd<1>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 2: return launch_fwd<2>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 3: return launch_fwd<3>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 4: return launch_fwd<4>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 5: case 6: return launch_fwd<6>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      default: return launch_fwd<8>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+    }
+  }
+  ln_fwd_block_kernel<<<(unsigned)rows, 256, 0, st>>>(x, gamma, beta, residual, y,
+                                                      (__nv_bfloat16*)y_bf16, mean, var, rows, d, eps);
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t npt_layernorm_bwd_workspace_bytes(int64_t rows, int32_t d) {
+  // sized for the larger of the two grid choices
+  int64_t nb = (int64_t)sm_count() * 2;
+  return (size_t)nb * 2 * (size_t)d * sizeof(float);
+}
+
+int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, const float* var,
+                      const float* dy, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                      int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  NPT_REQUIRE(rows > 0 && d > 0, "layernorm_bwd: bad shape rows=%lld d=%d", (long long)rows, d);
+  NPT_REQUIRE(workspace && workspace_bytes >= npt_layernorm_bwd_workspace_bytes(rows, d),
+              "layernorm_bwd: workspace too small (%zu < %zu)", workspace_bytes,
+              npt_layernorm_bwd_workspace_bytes(rows, d));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = (float*)workspace;
+  int nblocks;
+  const bool vec = (d % 4 == 0) && d <= kLnMaxVec * 128 && aligned16(x) && aligned16(dy) &&
+                   aligned16(dx) && aligned16(gamma) && (!dx_bf16 || aligned8(dx_bf16)) &&
+                   (size_t)kLnWarps * 2 * d * sizeof(float) <= 200 * 1024;
+  if (vec) {
+    nblocks = ln_bwd_blocks(rows);
+    const int nv = (int)cdiv(d, 128);
+    int rc;
+    switch (nv) {
+      case 1: rc = launch_bwd<1>(x, gamma, mean, var, dy, dx, dx_bf16, partial, nblocks, rows, d, eps, st); break;
+      case 2: rc = launch_bwd<2>(x, gamma, mean, var, dy, dx, dx_bf16, partial, nblocks, rows, d, eps, st); break;
+      case 3: rc = launch_bwd<3>(x, gamma, mean, var, dy, dx, dx_bf16, partial, nblocks, rows, d, eps, st); break;
+      case 4: rc = launch_bwd<4>(x, gamma, mean, var, dy, dx, dx_bf16, partial, nblocks, rows, d, eps, st); break;
+      case 5: case 6: rc = launch_bwd<6>(x, gamma, mean, var, dy, dx, dx_bf16, partial, nblocks, rows, d, eps, st); break;
+      default: rc = launch_bwd<8>(x, gamma, mean, var, dy, dx, dx_bf16, partial, nblocks, rows, d, eps, st); break;
+    }
+    if (rc) return rc;
+  } else {
+    int64_t cap = (int64_t)sm_count() * 2;
+    nblocks = (int)(rows < cap ? rows : cap);
+    ln_bwd_block_kernel<<<nblocks, 256, 0, st>>>(x, gamma, mean, var, dy, dx,
+                                                  (__nv_bfloat16*)dx_bf16, partial, rows, d, eps);
+    NPT_LAUNCH_CHECK();
+  }
+  const int threads = 256;
+  reduce_partials_kernel<<<(unsigned)cdiv(2 * (int64_t)d, threads), threads, 0, st>>>(
+      partial, dgamma, dbeta, nblocks, d);
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+"""Causal multi-head attention — drop-in for the reference's nn/attention.py.
+
+Faithful to the reference's arithmetic: the QKV projection's columns are laid out
+per head as [q_h | k_h | v_h]; the score scale is 1/sqrt(d_model) (FULL model width); the local
+head count is n_heads // tp_size with no divisibility check.  Heads are never transposed or
+copied: every product is a strided-batched GEMM that addresses the (B,S,h,3,Dh) projection
+output in place and writes straight into the merged (B,S,h*Dh) / (B,S,h,3,Dh) layouts.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import distributed as npdist
+from .. import ops
+from .. import runtime as rt
+from .activation import Softmax
+from .linear import Linear
+from .model import Model
+
+
+class Attention(Model):
+    def __init__(self, d_model: int, n_heads: int, d_hidden: int, **kwargs):
+        super().__init__()
+        self.add_layer("qkv_projection", Linear(d_model, n_heads * d_hidden * 3, weight_shard_axis=1,
+                                                use_bias=False, **kwargs))
+        self.add_layer("out_projection", Linear(n_heads * d_hidden, d_model, weight_shard_axis=0,
+                                                use_bias=False, **kwargs))
+        self.add_layer("softmax", Softmax(axis=-1))
+        self.add_settings({"d_model": d_model, "n_heads": n_heads, "d_hidden": d_hidden})
+
+    def _local_heads(self) -> int:
+        return self.n_heads if not self.is_scattered else self.n_heads // npdist.tensor_parallel_size()
+
+    @staticmethod
+    def _operand(t):
+        """(tensor, row pitch) of an activation in the precision the GEMM runs in."""
+        if rt.is_bf16():
+            sh = rt.bf16_of(t) if hasattr(t, "_npt_bf16") else ops.cast_bf16(t, pad_cols=True)
+            rt.attach_bf16(t, sh)
+            return sh
+        return t
+
+    def forward(self, inputs):
+        batch_size, seq_len, d_model = inputs.shape
+        h = self._local_heads()
+        qkv = self.qkv_projection.forward(inputs, want_bf16=True)          # (B,S,h*3*Dh)
+        ld = qkv.shape[-1]
+        dh3 = ld // h
+        dh = dh3 // 3
+        divisor = float(np.float32(d_model**0.5))                           # attention.py:48
+        nb = batch_size * h
+        q_op = self._operand(qkv)
+        head = (seq_len * ld, dh3)                                          # (batch, head) strides in qkv
+        mat = (h * seq_len * seq_len, seq_len * seq_len)                    # ... in (B,h,S,S)
+
+        scores = rt.empty((batch_size, h, seq_len, seq_len))               # q @ k^T
+        ops.gemm(q_op, q_op, seq_len, seq_len, dh, lda=ld, ldb=ld, trans_b=True, a_off=0, b_off=dh,
+                 a_strides=head, b_strides=head, C_out=scores, ldc=seq_len, c_strides=mat,
+                 batch=nb, batch_inner=h)
+        attention_weights = self.softmax.forward(scores, divisor=divisor)   # scale, mask, softmax
+        p_op = self._operand(attention_weights)
+
+        attention = rt.empty((batch_size, seq_len, h * dh))                 # p @ v, heads merged in place
+        att_b = rt.empty((batch_size, seq_len, h * dh), attention_dtype()) if rt.is_bf16() else None
+        merged = (seq_len * h * dh, dh)
+        ops.gemm(p_op, q_op, seq_len, dh, seq_len, lda=seq_len, ldb=ld, b_off=2 * dh, a_strides=mat,
+                 b_strides=head, C_out=attention, ldc=h * dh, c_strides=merged,
+                 Cb_out=att_b, ldcb=h * dh, cb_strides=merged, batch=nb, batch_inner=h)
+        if att_b is not None:
+            rt.attach_bf16(attention, att_b)
+        outputs = self.out_projection.forward(attention)
+
+        self.ctx |= {"qkv": qkv, "attention_weights": attention_weights, "shape": (batch_size, seq_len, h, dh)}
+        if self.is_scattered and npdist.tensor_parallel_size() > 1:
+            npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
+        return outputs
+
+    def backward(self, d_out):
+        batch_size, seq_len, h, dh = self.ctx.pop("shape")
+        qkv = self.ctx.pop("qkv")
+        p = self.ctx.pop("attention_weights")
+        ld = h * 3 * dh
+        nb = batch_size * h
+        head = (seq_len * ld, 3 * dh)
+        mat = (h * seq_len * seq_len, seq_len * seq_len)
+        merged = (seq_len * h * dh, dh)
+
+        d_att = self.out_projection.backward(d_out, want_bf16=True)         # (B,S,h*Dh)
+        qkv_op, p_op, datt_op = self._operand(qkv), self._operand(p), self._operand(d_att)
+        d_qkv = rt.empty((batch_size, seq_len, ld))
+        d_qkv_b = rt.empty((batch_size, seq_len, ld), attention_dtype()) if rt.is_bf16() else None
+
+        def into_qkv(col):
+            return dict(C_out=d_qkv, ldc=ld, c_off=col, c_strides=head,
+                        Cb_out=d_qkv_b, ldcb=ld, cb_off=col, cb_strides=head)
+
+        # dV = P^T @ dAtt                                                    (attention.py:81-83)
+        ops.gemm(p_op, datt_op, seq_len, dh, seq_len, lda=seq_len, ldb=h * dh, trans_a=True, a_strides=mat,
+                 b_strides=merged, batch=nb, batch_inner=h, **into_qkv(2 * dh))
+        # dP = dAtt @ V^T                                                    (attention.py:84)
+        d_p = rt.empty((batch_size, h, seq_len, seq_len))
+        ops.gemm(datt_op, qkv_op, seq_len, seq_len, dh, lda=h * dh, ldb=ld, trans_b=True, b_off=2 * dh,
+                 a_strides=merged, b_strides=head, C_out=d_p, ldc=seq_len, c_strides=mat, batch=nb, batch_inner=h)
+        # dS = softmax backward, masked, / sqrt(d_model)                     (attention.py:86-87)
+        self.softmax.ctx["outputs"] = p
+        d_s = self.softmax.backward(d_p)
+        ds_op = self._operand(d_s)
+        # dQ = dS @ K ; dK = dS^T @ Q                                        (attention.py:89-92)
+        ops.gemm(ds_op, qkv_op, seq_len, dh, seq_len, lda=seq_len, ldb=ld, b_off=dh, a_strides=mat, b_strides=head,
+                 batch=nb, batch_inner=h, **into_qkv(0))
+        ops.gemm(ds_op, qkv_op, seq_len, dh, seq_len, lda=seq_len, ldb=ld, trans_a=True, b_off=0, a_strides=mat,
+                 b_strides=head, batch=nb, batch_inner=h, **into_qkv(dh))
+        if d_qkv_b is not None:
+            rt.attach_bf16(d_qkv, d_qkv_b)
+        d_in = self.qkv_projection.backward(d_qkv)
+        if self.is_scattered and npdist.tensor_parallel_size() > 1:
+            npdist.all_reduce(d_in, group=npdist.tensor_parallel_group())
+        return d_in
+
+
+def attention_dtype():
+    import torch
+
+    return torch.bfloat16

@@ -1,0 +1,84 @@
+"""GEMM-level helpers shared by Linear / MLP / Attention / OutputEmbedding.
+
+Each helper is one `npt_gemm` call (plus a bf16 cast of an operand when no shadow exists yet).
+fp32 mode -> the FFMA kernel on fp32 operands; bf16 mode -> the tcgen05 kernel on bf16 shadows
+with fp32 accumulation and fp32 outputs (bf16 operands only, fp32 residual stream).
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from .. import runtime as rt
+
+_BF16 = torch.bfloat16
+
+
+def _act(x: torch.Tensor):
+    """(operand tensor, leading dimension) of an activation for the current precision."""
+    if rt.is_bf16():
+        sh = getattr(x, "_npt_bf16", None)
+        if sh is None:
+            sh = ops.cast_bf16(x, pad_cols=True)
+            rt.attach_bf16(x, sh)
+        return sh, sh.shape[-1]
+    return x, x.shape[-1]
+
+
+def _weight(layer, name: str):
+    p = getattr(layer, name).data
+    if rt.is_bf16():
+        sh = layer.shadow(name)
+        return sh, sh.shape[-1]
+    return p, p.stride(0)
+
+
+def linear_forward(x, layer, wname="weight", bias=None, relu=False, want_bf16=False):
+    """y = x @ W (+ b) (ReLU) — nn/linear.py:44-47.  x (..., d_in), W (d_in, d_out)."""
+    W = getattr(layer, wname).data
+    d_in, d_out = W.shape
+    T = x.numel() // d_in
+    A, lda = _act(x)
+    B, ldb = _weight(layer, wname)
+    y = rt.empty((*x.shape[:-1], d_out))
+    yb = rt.empty((*x.shape[:-1], d_out), _BF16) if (want_bf16 and rt.is_bf16() and d_out % 8 == 0) else None
+    ops.gemm(A, B, T, d_out, d_in, lda=lda, ldb=ldb, C_out=y, ldc=d_out, Cb_out=yb, ldcb=d_out, bias=bias, relu=relu)
+    if yb is not None:
+        rt.attach_bf16(y, yb)
+    return y
+
+
+def linear_backward_weight(x, dy):
+    """dW = x^T @ dy over all tokens — einsum("bsd,bsh->dh"), nn/linear.py:55."""
+    d_in, d_out = x.shape[-1], dy.shape[-1]
+    T = x.numel() // d_in
+    A, lda = _act(x)
+    B, ldb = _act(dy)
+    dW = rt.empty((d_in, d_out))
+    ops.gemm(A, B, d_in, d_out, T, lda=lda, ldb=ldb, trans_a=True, C_out=dW, ldc=d_out)
+    return dW
+
+
+def linear_backward_input(dy, layer, wname="weight", mask=None, want_bf16=False):
+    """dx = dy @ W^T (optionally * (mask > 0): the fused ReLU.backward) — nn/linear.py:60."""
+    W = getattr(layer, wname).data
+    d_in, d_out = W.shape
+    T = dy.numel() // d_out
+    A, lda = _act(dy)
+    B, ldb = _weight(layer, wname)
+    dx = rt.empty((*dy.shape[:-1], d_in))
+    dxb = rt.empty((*dy.shape[:-1], d_in), _BF16) if (want_bf16 and rt.is_bf16() and d_in % 8 == 0) else None
+    mk, ldm = (None, 0)
+    if mask is not None:
+        mk, ldm = mask, mask.shape[-1]
+    ops.gemm(A, B, T, d_in, d_out, lda=lda, ldb=ldb, trans_b=True, C_out=dx, ldc=d_in, Cb_out=dxb, ldcb=d_in,
+             mask=mk, ldmask=ldm)
+    if dxb is not None:
+        rt.attach_bf16(dx, dxb)
+    return dx
+
+
+def bias_grad(dy):
+    """db = dy.sum(axis=(0,1)) — nn/linear.py:57-58."""
+    n = dy.shape[-1]
+    return ops.colsum(dy.numel() // n, n, dy)

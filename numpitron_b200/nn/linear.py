@@ -1,0 +1,36 @@
+"""Linear — drop-in for the reference's nn/linear.py (same constructor, forward, backward)."""
+from __future__ import annotations
+
+from . import functional as F
+from .core import Layer, weight_init_fn
+
+
+class Linear(Layer):
+    def __init__(self, d_in: int, d_out: int, use_bias: bool = True, weight_shard_axis: int | None = None,
+                 bias_shard_axis: int | None = None, weight_init: str = "scaled_normal", bias_init: str = "zeros",
+                 **kwargs):
+        super().__init__()
+        self.add_settings({"d_in": d_in, "d_out": d_out, "use_bias": use_bias,
+                           "weight_shard_axis": weight_shard_axis, "bias_shard_axis": bias_shard_axis,
+                           "weight_init": weight_init, "bias_init": bias_init})
+        scale = kwargs.pop("scale", 0.006)  # nn/linear.py:31
+        self.add_parameter("weight", weight_init_fn(weight_init, **kwargs, scale=scale)((d_in, d_out)),
+                           weight_shard_axis)
+        if self.use_bias:
+            self.add_parameter("bias", weight_init_fn(bias_init, **kwargs)((d_out,)), bias_shard_axis)
+
+    # MLP fuses ReLU into this layer's epilogues through the two keyword hooks.
+    def forward(self, inputs, relu: bool = False, want_bf16: bool = False):
+        """outputs = inputs @ W (+ b) — one GEMM with the bias (and ReLU) in its epilogue."""
+        bias = self.bias.data if self.use_bias else None
+        outputs = F.linear_forward(inputs, self, "weight", bias=bias, relu=relu, want_bf16=want_bf16)
+        self.ctx["inputs"] = inputs
+        return outputs
+
+    def backward(self, d_out, mask=None, want_bf16: bool = False):
+        """dW = x^T dy (replaces, never accumulates), db = sum dy, returns dx = dy W^T."""
+        inputs = self.ctx.pop("inputs")
+        self.update_parameter("weight", gradient=F.linear_backward_weight(inputs, d_out))
+        if self.use_bias:
+            self.update_parameter("bias", gradient=F.bias_grad(d_out))
+        return F.linear_backward_input(d_out, self, "weight", mask=mask, want_bf16=want_bf16)

@@ -1,0 +1,38 @@
+"""MLP: column-parallel Linear -> ReLU -> row-parallel Linear -> TP all-reduce.
+Drop-in for the reference's nn/mlp.py; the ReLU lives in the GEMM epilogues."""
+from __future__ import annotations
+
+from .. import distributed as npdist
+from .. import runtime as rt
+from .activation import ReLU
+from .linear import Linear
+from .model import Model
+
+
+class MLP(Model):
+    def __init__(self, d_in: int, d_hidden: int, d_out: int, **kwargs):
+        super().__init__()
+        self.add_settings({"d_in": d_in, "d_hidden": d_hidden, "d_out": d_out})
+        self.add_layer("column_linear", Linear(d_in=d_in, d_out=d_hidden, weight_shard_axis=1, bias_shard_axis=0, **kwargs))
+        self.add_layer("row_linear", Linear(d_in=d_hidden, d_out=d_out, weight_shard_axis=0, **kwargs))
+        self.add_layer("relu", ReLU())
+        # Only TP rank 0 adds the row-linear bias (mlp.py:35); the parameter exists everywhere.
+        self.row_linear.use_bias = npdist.tensor_parallel_rank() == 0
+
+    def forward(self, inputs):
+        # max(0, x@W1+b1) in one GEMM epilogue; the post-ReLU tensor doubles as the backward mask
+        # because relu(a) > 0  <=>  a > 0.
+        hidden = self.column_linear.forward(inputs, relu=True, want_bf16=True)
+        outputs = self.row_linear.forward(hidden)
+        if self.is_scattered and npdist.tensor_parallel_size() > 1:
+            npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
+        return outputs
+
+    def backward(self, d_out):
+        hidden = self.row_linear.ctx["inputs"]
+        mask = rt.bf16_of(hidden) if rt.is_bf16() and hasattr(hidden, "_npt_bf16") else hidden
+        d_out = self.row_linear.backward(d_out, mask=mask, want_bf16=True)  # (dy@W2^T) * (a>0)
+        d_out = self.column_linear.backward(d_out)
+        if self.is_scattered and npdist.tensor_parallel_size() > 1:
+            npdist.all_reduce(d_out, group=npdist.tensor_parallel_group())
+        return d_out

@@ -1,0 +1,32 @@
+"""LayerNorm — drop-in for the reference's nn/normalization.py."""
+from __future__ import annotations
+
+from .. import ops
+from .. import runtime as rt
+from .core import Layer, weight_init_fn
+
+
+class LayerNorm(Layer):
+    def __init__(self, d_model: int, eps: float = 1e-5, weight_init: str = "scaled_normal",
+                 bias_init: str = "zeros", **kwargs):
+        super().__init__()
+        scale = kwargs.pop("scale", 0.2)  # nn/normalization.py:17 — weight is NOT ones
+        self.add_settings({"d_model": d_model, "eps": eps})
+        self.add_parameter("weight", weight_init_fn(weight_init, **kwargs, scale=scale)((d_model,)))
+        self.add_parameter("bias", weight_init_fn(bias_init, **kwargs)((d_model,)))
+
+    def forward(self, inputs, residual=None):
+        """gamma*(x-mean)/sqrt(var+eps)+beta, optionally + residual in the same pass
+        (TransformerBlock's `norm(sub(x)) + x`, transformer_block.py:20-21)."""
+        outputs, mean, var = ops.layernorm_fwd(inputs, self.weight.data, self.bias.data, self.eps,
+                                               residual=residual, want_bf16=rt.is_bf16())
+        self.ctx |= {"inputs": inputs, "mean": mean, "var": var}
+        return outputs
+
+    def backward(self, d_out):
+        inputs, mean, var = self.ctx.pop("inputs"), self.ctx.pop("mean"), self.ctx.pop("var")
+        d_in, d_weight, d_bias = ops.layernorm_bwd(inputs, self.weight.data, mean, var, d_out, self.eps,
+                                                   want_bf16=rt.is_bf16())
+        self.update_parameter("weight", gradient=d_weight)
+        self.update_parameter("bias", gradient=d_bias)
+        return d_in

@@ -1,0 +1,39 @@
+"""Transformer — drop-in for the reference's nn/transformer.py."""
+from __future__ import annotations
+
+from functools import partial
+
+from .. import distributed as npdist
+from .embedding import InputEmbedding, OutputEmbedding, PositionalEncoding
+from .model import Model
+from .transformer_block import TransformerBlock
+
+
+class Transformer(Model):
+    def __init__(self, d_model: int, n_heads: int, n_layers: int, vocab_size: int, seq_len: int, **kwargs):
+        super().__init__()
+        self.add_settings({"d_model": d_model, "n_heads": n_heads, "n_layers": n_layers,
+                           "vocab_size": vocab_size, "seq_len": seq_len})
+        block = partial(TransformerBlock, d_model, n_heads, **kwargs)
+        self.add_layer("input_embedding", InputEmbedding(d_model, vocab_size, **kwargs))
+        self.add_layer("positional_encoding", PositionalEncoding(d_model, seq_len, **kwargs))
+        for layer in range(n_layers):
+            self.add_layer(f"block_{layer}", block())
+        self.add_layer("output_embedding", OutputEmbedding(self.input_embedding))  # tied
+
+    def backward(self, d_out):
+        """Reverse pass; after each TOP-LEVEL layer its own parameters are all-reduced (SUM) over the
+        data-parallel group — which in practice is only the tied embedding gradient, because a
+        TransformerBlock's own `parameters` dict is empty (reference: transformer.py:48-59, Q11)."""
+        for layer in list(self.layers.values())[::-1]:
+            d_out = layer.backward(d_out)
+            if npdist.data_parallel_size() > 1:
+                for parameter in layer.parameters.values():
+                    npdist.all_reduce(parameter.gradient, group=npdist.data_parallel_group())
+        return d_out
+
+    @classmethod
+    def from_dict(cls, model_dict: dict[str, dict]):
+        transformer = super().from_dict(model_dict)
+        transformer.output_embedding.input_embedding = transformer.input_embedding  # tie
+        return transformer

@@ -1,0 +1,292 @@
+"""Thin Python wrappers: torch buffers in, one C-ABI call each, torch buffers out.
+
+Nothing here computes: every function marshals pointers/sizes into `libnumpitron_b200.so`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from . import runtime as rt
+from ._lib import AdamTensor, GemmArgs, check
+
+_F32, _BF16, _U16 = torch.float32, torch.bfloat16, torch.uint16
+
+
+def _lib_():
+    rt.require_gpu("kernel call")
+    return _lib.load()
+
+
+def _p(t, off=0):
+    return rt.ptr(t, off)
+
+
+# ---- GEMM ----------------------------------------------------------------------------------------
+def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_off=0,
+         a_strides=(0, 0), b_strides=(0, 0), C_out=None, ldc=0, c_off=0, c_strides=(0, 0),
+         Cb_out=None, ldcb=0, cb_off=0, cb_strides=(0, 0), batch=1, batch_inner=1, alpha=1.0,
+         bias=None, relu=False, mask=None, ldmask=0, mask_off=0, mask_strides=(0, 0), mode=None):
+    """C[b] = alpha * op(A[b]) op(B[b]) (+bias)(ReLU)(*mask>0) — see npt_gemm in the header.
+
+    strides are (outer, inner) in elements.  A/B must be fp32 for mode 0 and bf16 for mode 1.
+    """
+    lib = _lib_()
+    mode = rt.gemm_mode() if mode is None else mode
+    want = _BF16 if mode == 1 else _F32
+    if A.dtype != want or B.dtype != want:
+        raise TypeError(f"gemm mode {mode} needs {want} operands, got {A.dtype}/{B.dtype}")
+    g = GemmArgs()
+    g.mode, g.trans_a, g.trans_b = mode, int(trans_a), int(trans_b)
+    g.M, g.N, g.K = M, N, K
+    g.batch, g.batch_inner = batch, batch_inner
+    g.A, g.lda, g.stride_a_outer, g.stride_a_inner = _p(A, a_off), lda, a_strides[0], a_strides[1]
+    g.B, g.ldb, g.stride_b_outer, g.stride_b_inner = _p(B, b_off), ldb, b_strides[0], b_strides[1]
+    if C_out is not None:
+        assert C_out.dtype == _F32
+        g.C, g.ldc, g.stride_c_outer, g.stride_c_inner = _p(C_out, c_off), ldc, c_strides[0], c_strides[1]
+    if Cb_out is not None:
+        assert Cb_out.dtype == _BF16
+        g.C_bf16, g.ldcb, g.stride_cb_outer, g.stride_cb_inner = _p(Cb_out, cb_off), ldcb, cb_strides[0], cb_strides[1]
+    g.alpha = alpha
+    g.bias = _p(bias)
+    g.relu = int(relu)
+    if mask is not None:
+        g.mask, g.mask_is_bf16 = _p(mask, mask_off), int(mask.dtype == _BF16)
+        g.ldmask, g.stride_mask_outer, g.stride_mask_inner = ldmask, mask_strides[0], mask_strides[1]
+    need = lib.npt_gemm_workspace_bytes(C.byref(g))
+    if need:
+        ws = rt.workspace(need)
+        g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
+    check(lib.npt_gemm(C.byref(g), rt.stream()), "npt_gemm")
+
+
+def cast_bf16(t: torch.Tensor, pad_cols: bool = False) -> torch.Tensor:
+    """bf16 copy of a contiguous fp32 tensor; with pad_cols the last dim is padded to a multiple of 8."""
+    lib = _lib_()
+    assert t.dtype == _F32 and t.is_contiguous()
+    cols = t.shape[-1]
+    rows = t.numel() // cols
+    ld = rt.pad8(cols) if pad_cols else cols
+    out = rt.empty((*t.shape[:-1], ld), _BF16)
+    check(lib.npt_cast_f32_bf16(_p(t), cols, _p(out), ld, rows, cols, rt.stream()), "npt_cast_f32_bf16")
+    return out
+
+
+# ---- LayerNorm -----------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, residual=None, want_bf16=False):
+    lib = _lib_()
+    d = x.shape[-1]
+    rows = x.numel() // d
+    y = rt.empty(x.shape)
+    yb = rt.empty(x.shape, _BF16) if want_bf16 else None
+    mean, var = rt.empty((rows,)), rt.empty((rows,))
+    check(lib.npt_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(residual), _p(y), _p(yb), _p(mean), _p(var),
+                                rows, d, eps, rt.stream()), "npt_layernorm_fwd")
+    if yb is not None:
+        rt.attach_bf16(y, yb)
+    return y, mean, var
+
+
+def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False):
+    lib = _lib_()
+    d = x.shape[-1]
+    rows = x.numel() // d
+    dx = rt.empty(x.shape)
+    dxb = rt.empty(x.shape, _BF16) if want_bf16 else None
+    dgamma, dbeta = rt.empty((d,)), rt.empty((d,))
+    need = lib.npt_layernorm_bwd_workspace_bytes(rows, d)
+    ws = rt.workspace(need)
+    check(lib.npt_layernorm_bwd(_p(x), _p(gamma), _p(mean), _p(var), _p(dy), _p(dx), _p(dxb), _p(dgamma), _p(dbeta),
+                                rows, d, eps, ws.data_ptr(), ws.numel(), rt.stream()), "npt_layernorm_bwd")
+    if dxb is not None:
+        rt.attach_bf16(dx, dxb)
+    return dx, dgamma, dbeta
+
+
+# ---- ReLU / column sum ---------------------------------------------------------------------------
+def relu_fwd(x, want_bf16=False):
+    lib = _lib_()
+    y = rt.empty(x.shape)
+    yb = rt.empty(x.shape, _BF16) if want_bf16 else None
+    check(lib.npt_relu_fwd(_p(x), _p(y), _p(yb), x.numel(), rt.stream()), "npt_relu_fwd")
+    if yb is not None:
+        rt.attach_bf16(y, yb)
+    return y
+
+
+def relu_bwd(x, dy, want_bf16=False):
+    lib = _lib_()
+    dx = rt.empty(x.shape)
+    dxb = rt.empty(x.shape, _BF16) if want_bf16 else None
+    check(lib.npt_relu_bwd(_p(x), _p(dy), _p(dx), _p(dxb), x.numel(), rt.stream()), "npt_relu_bwd")
+    if dxb is not None:
+        rt.attach_bf16(dx, dxb)
+    return dx
+
+
+def colsum(x2d_rows: int, cols: int, x: torch.Tensor, ld: int | None = None) -> torch.Tensor:
+    lib = _lib_()
+    ld = cols if ld is None else ld
+    out = rt.empty((cols,))
+    need = lib.npt_colsum_workspace_bytes(x2d_rows, cols)
+    ws = rt.workspace(need)
+    check(lib.npt_colsum(_p(x), ld, _p(out), x2d_rows, cols, ws.data_ptr(), ws.numel(), rt.stream()), "npt_colsum")
+    return out
+
+
+# ---- causal softmax ----------------------------------------------------------------------------------
+def softmax_causal_fwd(scores, divisor, want_bf16=False):
+    lib = _lib_()
+    S = scores.shape[-1]
+    n_mats = scores.numel() // (S * S)
+    p = rt.empty(scores.shape)
+    pb = rt.empty(scores.shape, _BF16) if want_bf16 else None
+    check(lib.npt_softmax_causal_fwd(_p(scores), _p(p), _p(pb), n_mats, S, divisor, rt.stream()), "npt_softmax_causal_fwd")
+    if pb is not None:
+        rt.attach_bf16(p, pb)
+    return p
+
+
+def softmax_causal_bwd(p, dp, divisor, want_bf16=False):
+    lib = _lib_()
+    S = p.shape[-1]
+    n_mats = p.numel() // (S * S)
+    ds = rt.empty(p.shape)
+    dsb = rt.empty(p.shape, _BF16) if want_bf16 else None
+    check(lib.npt_softmax_causal_bwd(_p(p), _p(dp), _p(ds), _p(dsb), n_mats, S, divisor, rt.stream()), "npt_softmax_causal_bwd")
+    if dsb is not None:
+        rt.attach_bf16(ds, dsb)
+    return ds
+
+
+# ---- embeddings ----------------------------------------------------------------------------------------
+def embedding_gather(tokens, E, pos, S, chunk_start, chunk_end, masked, want_bf16=False):
+    lib = _lib_()
+    assert tokens.dtype == _U16 and E.dtype == _F32
+    d, ldE = E.shape[0], E.stride(0)
+    T = tokens.numel()
+    out = rt.empty((*tokens.shape, d))
+    ob = rt.empty((*tokens.shape, d), _BF16) if want_bf16 else None
+    check(lib.npt_embedding_gather(_p(tokens), _p(E), ldE, _p(pos), _p(out), _p(ob), T, S, d, chunk_start, chunk_end,
+                                   int(masked), rt.stream()), "npt_embedding_gather")
+    if ob is not None:
+        rt.attach_bf16(out, ob)
+    return out
+
+
+def add_pos(x, pos, S, want_bf16=False):
+    """pos[:S] + x into a new buffer (x is left untouched, as in the reference)."""
+    lib = _lib_()
+    d = x.shape[-1]
+    T = x.numel() // d
+    out = rt.empty(x.shape)
+    ob = rt.empty(x.shape, _BF16) if want_bf16 else None
+    check(lib.npt_add_pos(_p(x), _p(pos), _p(out), _p(ob), T, S, d, rt.stream()), "npt_add_pos")
+    if ob is not None:
+        rt.attach_bf16(out, ob)
+    return out
+
+
+def embedding_scatter_add(tokens, d_out, grad, chunk_start, chunk_end, masked):
+    """In place on `grad` (d, V_local)."""
+    lib = _lib_()
+    assert tokens.dtype == _U16
+    d, V_local, ldG = grad.shape[0], grad.shape[1], grad.stride(0)
+    T = tokens.numel()
+    need = lib.npt_embedding_scatter_add_workspace_bytes(T, V_local)
+    ws = rt.workspace(need)
+    check(lib.npt_embedding_scatter_add(_p(tokens), _p(d_out), _p(grad), ldG, T, d, V_local, chunk_start, chunk_end,
+                                        int(masked), ws.data_ptr(), ws.numel(), rt.stream()), "npt_embedding_scatter_add")
+    return grad
+
+
+# ---- loss ------------------------------------------------------------------------------------------------
+def softmax_ce_fused(logits, labels, chunk_start, chunk_end, want_bf16=False):
+    lib = _lib_()
+    V = logits.shape[-1]
+    T = logits.numel() // V
+    loss = rt.empty(labels.shape)
+    grad = rt.empty(logits.shape)
+    ldgb = rt.pad8(V)
+    gb = rt.empty((*logits.shape[:-1], ldgb), _BF16) if want_bf16 else None
+    check(lib.npt_softmax_ce_fused(_p(logits), V, _p(labels), _p(loss), _p(grad), V, _p(gb), ldgb, T, V, chunk_start,
+                                   chunk_end, rt.stream()), "npt_softmax_ce_fused")
+    if gb is not None:
+        rt.attach_bf16(grad, gb)
+    return loss, grad
+
+
+def softmax_ce_stage1(logits):
+    lib = _lib_()
+    V = logits.shape[-1]
+    T = logits.numel() // V
+    rowmax = rt.empty((T,))
+    check(lib.npt_softmax_ce_stage1(_p(logits), V, _p(rowmax), T, V, rt.stream()), "npt_softmax_ce_stage1")
+    return rowmax
+
+
+def softmax_ce_stage2(logits, labels, rowmax, chunk_start, chunk_end):
+    lib = _lib_()
+    V = logits.shape[-1]
+    T = logits.numel() // V
+    picked, sumexp = rt.empty((T,)), rt.empty((T,))
+    check(lib.npt_softmax_ce_stage2(_p(logits), V, _p(labels), _p(rowmax), _p(picked), _p(sumexp), T, V, chunk_start,
+                                    chunk_end, rt.stream()), "npt_softmax_ce_stage2")
+    return picked, sumexp
+
+
+def softmax_ce_stage3(logits, labels, rowmax, picked, sumexp, chunk_start, chunk_end, want_bf16=False):
+    lib = _lib_()
+    V = logits.shape[-1]
+    T = logits.numel() // V
+    loss = rt.empty(labels.shape)
+    grad = rt.empty(logits.shape)
+    ldgb = rt.pad8(V)
+    gb = rt.empty((*logits.shape[:-1], ldgb), _BF16) if want_bf16 else None
+    check(lib.npt_softmax_ce_stage3(_p(logits), V, _p(labels), _p(rowmax), _p(picked), _p(sumexp), _p(loss), _p(grad), V,
+                                    _p(gb), ldgb, T, V, chunk_start, chunk_end, rt.stream()), "npt_softmax_ce_stage3")
+    if gb is not None:
+        rt.attach_bf16(grad, gb)
+    return loss, grad
+
+
+def mean(x):
+    lib = _lib_()
+    out = rt.empty((1,))
+    check(lib.npt_mean(_p(x), _p(out), x.numel(), rt.stream()), "npt_mean")
+    return out
+
+
+# ---- Adam ------------------------------------------------------------------------------------------------
+class AdamTable:
+    """Host + device copies of the npt_adam_tensor table for one optimizer."""
+
+    def __init__(self, entries):
+        """entries: list of (p, g, m, v, shadow_or_None) torch tensors."""
+        n = len(entries)
+        self.n = n
+        self.host = (AdamTensor * max(n, 1))()
+        self.keep = entries
+        for i, (p, g, m, v, sh) in enumerate(entries):
+            t = self.host[i]
+            t.p, t.g, t.m, t.v = _p(p), _p(g), _p(m), _p(v)
+            t.n = p.numel()
+            if sh is not None:
+                t.p_bf16 = _p(sh)
+                t.shadow_cols = p.shape[-1]
+                t.shadow_ld = sh.shape[-1]
+        raw = bytes(self.host)
+        # pinned staging so the upload is a capturable async memcpy (CUDA-graph safe)
+        self.pinned = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone().pin_memory()
+        self.dev = torch.empty(len(raw), dtype=torch.uint8, device=rt.device())
+        self.dev.copy_(self.pinned, non_blocking=True)
+        self.key = tuple((_p(p), _p(g), _p(m), _p(v), _p(sh)) for p, g, m, v, sh in entries)
+
+
+def adam_step(table: AdamTable, lr, b1, omb1, b2, omb2, c1, c2, eps):
+    lib = _lib_()
+    check(lib.npt_adam_step(table.dev.data_ptr(), table.host, table.n, lr, b1, omb1, b2, omb2, c1, c2, eps, rt.stream()),
+          "npt_adam_step")

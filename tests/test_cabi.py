@@ -1,0 +1,89 @@
+"""CPU-side checks of the C-ABI boundary: the shared object loads, exports every symbol that
+include/numpitron_b200.h declares, the ctypes table covers them all, and host-only entry points
+(error text, workspace sizing, argument validation) behave.  No kernel is launched here."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+from numpitron_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "numpitron_b200.h"
+
+
+def header_functions():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(npt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+
+
+def test_ctypes_table_matches_header():
+    assert sorted(_lib.declared_symbols()) == header_functions()
+
+
+def test_struct_layouts_match_header():
+    # sizes the C compiler gives the two argument structs (LP64): see include/numpitron_b200.h
+    assert C.sizeof(_lib.GemmArgs) == 8 * 4 + 4 * 32 + 8 + 8 + 8 + 8 + 8 + 3 * 8 + 16
+    assert C.sizeof(_lib.AdamTensor) == 64
+
+
+def test_version_and_error_text():
+    lib = _lib.load()
+    assert lib.npt_version() >= 100
+    rc = lib.npt_gemm(None, None)
+    assert rc != 0
+    assert b"null args" in lib.npt_last_error()
+
+
+def test_gemm_argument_validation_and_workspace_sizing():
+    lib = _lib.load()
+    g = _lib.GemmArgs()
+    g.mode, g.M, g.N, g.K, g.batch, g.batch_inner = 0, 0, 8, 8, 1, 1
+    assert lib.npt_gemm(C.byref(g), None) != 0 and b"bad shape" in lib.npt_last_error()
+    # dW-shaped problem (small M x N, long K) asks for split-K scratch; a big square one does not
+    g.M, g.N, g.K = 384, 1152, 16384
+    need = lib.npt_gemm_workspace_bytes(C.byref(g))
+    assert need > 0 and need % (384 * 1152 * 4) == 0
+    g.M, g.N, g.K = 16384, 1152, 384
+    assert lib.npt_gemm_workspace_bytes(C.byref(g)) == 0
+    g.mode = 1
+    g.M, g.N, g.K = 384, 1152, 16384
+    assert lib.npt_gemm_workspace_bytes(C.byref(g)) > 0
+
+
+def test_workspace_queries():
+    lib = _lib.load()
+    assert lib.npt_layernorm_bwd_workspace_bytes(16384, 384) >= 2 * 384 * 4
+    assert lib.npt_colsum_workspace_bytes(16384, 1536) >= 1536 * 4
+    assert lib.npt_embedding_scatter_add_workspace_bytes(16384, 65) >= 16384 * 4 + 2 * 66 * 4
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(_lib.NptError, match="no CPU/PyTorch fallback"):
+        _lib.load()
+
+
+def test_compute_refuses_to_run_without_gpu():
+    import numpy as np
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from numpitron_b200 import distributed as npdist
+    from numpitron_b200.nn import LayerNorm
+
+    npdist.init(tp_size=1)
+    ln = LayerNorm(32, rng=np.random.default_rng(0))
+    with pytest.raises(_lib.NptError, match="no CPU fallback"):
+        ln(np.zeros((1, 2, 32), np.float32))
