@@ -28,8 +28,16 @@ extern "C" {
 /* ---- library ------------------------------------------------------------------------- */
 const char* npt_last_error(void);
 int npt_version(void);
+/* Number of kernel launches this library has issued in this process (monotonic). */
+unsigned long long npt_launch_count(void);
 /* Fills SM count and compute capability of the current device. */
 int npt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Pinned host staging buffers and async copies for the step's inputs (uint16 tokens, as
+ * data/loader.py:48-54 yields them) and its scalar result.  kind: 1 = H2D, 2 = D2H, 3 = D2D. */
+int npt_pinned_alloc(void** out, size_t bytes);
+int npt_pinned_free(void* p);
+int npt_memcpy_async(void* dst, const void* src, size_t bytes, int32_t kind, void* stream);
 
 /* ---- dense contractions ---------------------------------------------------------------
  * One strided-batched GEMM serves every contraction on the path:

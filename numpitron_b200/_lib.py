@@ -51,7 +51,11 @@ _P = c_void_p
 _SIGNATURES = {
     "npt_last_error": (C.c_char_p, []),
     "npt_version": (c_int, []),
+    "npt_launch_count": (C.c_ulonglong, []),
     "npt_device_info": (c_int, [C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
+    "npt_pinned_alloc": (c_int, [C.POINTER(c_void_p), c_size_t]),
+    "npt_pinned_free": (c_int, [_P]),
+    "npt_memcpy_async": (c_int, [_P, _P, c_size_t, c_int32, _P]),
     "npt_gemm_workspace_bytes": (c_size_t, [C.POINTER(GemmArgs)]),
     "npt_gemm": (c_int, [C.POINTER(GemmArgs), _P]),
     "npt_cast_f32_bf16": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, _P]),

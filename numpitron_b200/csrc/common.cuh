@@ -29,7 +29,12 @@ void set_error(const char* fmt, ...);
     }                                         \
   } while (0)
 
-#define NPT_LAUNCH_CHECK() NPT_CHECK_CUDA(cudaGetLastError())
+void count_launch();
+#define NPT_LAUNCH_CHECK()                 \
+  do {                                     \
+    npt::count_launch();                   \
+    NPT_CHECK_CUDA(cudaGetLastError());    \
+  } while (0)
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

@@ -14,6 +14,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
 int sm_count() {
   static int cached = 0;
   if (cached == 0) {
@@ -35,12 +38,36 @@ const char* npt_last_error(void) { return npt::g_err; }
 
 int npt_version(void) { return 100; }
 
+unsigned long long npt_launch_count(void) { return npt::g_launches; }
+
 int npt_device_info(int* sm, int* major, int* minor) {
   int dev = 0;
   NPT_CHECK_CUDA(cudaGetDevice(&dev));
   NPT_CHECK_CUDA(cudaDeviceGetAttribute(sm, cudaDevAttrMultiProcessorCount, dev));
   NPT_CHECK_CUDA(cudaDeviceGetAttribute(major, cudaDevAttrComputeCapabilityMajor, dev));
   NPT_CHECK_CUDA(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return 0;
+}
+
+
+// Pinned host staging + async copies, owned by the caller.  Kept out of PyTorch's caching host
+// allocator on purpose: the copies are issued inside CUDA-graph capture.
+int npt_pinned_alloc(void** out, size_t bytes) {
+  NPT_REQUIRE(out != nullptr && bytes > 0, "pinned_alloc: bad arguments");
+  NPT_CHECK_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return 0;
+}
+
+int npt_pinned_free(void* p) {
+  if (p) NPT_CHECK_CUDA(cudaFreeHost(p));
+  return 0;
+}
+
+int npt_memcpy_async(void* dst, const void* src, size_t bytes, int32_t kind, void* stream) {
+  NPT_REQUIRE(kind == 1 || kind == 2 || kind == 3, "memcpy_async: kind must be 1 (H2D), 2 (D2H) or 3 (D2D)");
+  if (bytes == 0) return 0;
+  const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  NPT_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)stream));
   return 0;
 }
 

@@ -60,7 +60,19 @@ def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_of
     if need:
         ws = rt.workspace(need)
         g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
+    if GEMM_PROFILE is None:
+        check(lib.npt_gemm(C.byref(g), rt.stream()), "npt_gemm")
+        return
+    # bench.py's roofline leg: CUDA events around this launch, on the launching stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(lib.npt_gemm(C.byref(g), rt.stream()), "npt_gemm")
+    e1.record()
+    GEMM_PROFILE.append(dict(events=(e0, e1), flops=2.0 * M * N * K * batch, M=M, N=N, K=K, batch=batch,
+                             trans=(int(trans_a), int(trans_b)), mode=mode, splitk=bool(need)))
+
+
+GEMM_PROFILE = None  # set to a list to collect per-launch timings
 
 
 def cast_bf16(t: torch.Tensor, pad_cols: bool = False) -> torch.Tensor:
@@ -260,16 +272,63 @@ def mean(x):
     return out
 
 
+# ---- pinned staging ---------------------------------------------------------------------------------
+class PinnedBuffer:
+    """Page-locked host bytes owned by the library (not by torch's caching host allocator, whose
+    event bookkeeping breaks when the copies are issued under CUDA-graph capture)."""
+
+    def __init__(self, nbytes: int):
+        import numpy as np
+
+        lib = _lib_()
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(lib.npt_pinned_alloc(C.byref(p), self.nbytes), "npt_pinned_alloc")
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self.ptr))
+
+    def view(self, dtype, shape):
+        return self.array.view(dtype).reshape(shape)
+
+    def to_device(self, dst: torch.Tensor, nbytes: int | None = None):
+        check(_lib_().npt_memcpy_async(dst.data_ptr(), self.ptr, self.nbytes if nbytes is None else nbytes, 1,
+                                       rt.stream()), "npt_memcpy_async")
+
+    def from_device(self, src: torch.Tensor, nbytes: int | None = None):
+        check(_lib_().npt_memcpy_async(self.ptr, src.data_ptr(), self.nbytes if nbytes is None else nbytes, 2,
+                                       rt.stream()), "npt_memcpy_async")
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None):
+                _lib.load().npt_pinned_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
 # ---- Adam ------------------------------------------------------------------------------------------------
 class AdamTable:
-    """Host + device copies of the npt_adam_tensor table for one optimizer."""
+    """Host (pinned) + device copies of the npt_adam_tensor table for one optimizer."""
 
-    def __init__(self, entries):
-        """entries: list of (p, g, m, v, shadow_or_None) torch tensors."""
-        n = len(entries)
-        self.n = n
-        self.host = (AdamTensor * max(n, 1))()
-        self.keep = entries
+    def __init__(self, capacity: int):
+        self.capacity = max(int(capacity), 1)
+        self.host = (AdamTensor * self.capacity)()
+        self.pinned = PinnedBuffer(C.sizeof(self.host))
+        self.dev = torch.empty(C.sizeof(self.host), dtype=torch.uint8, device=rt.device())
+        self.n = 0
+        self.key = None
+        self.keep = None
+
+    def fill(self, entries):
+        """entries: list of (p, g, m, v, shadow_or_None).  Re-uploads only when a pointer changed."""
+        key = tuple((_p(p), _p(g), _p(m), _p(v), _p(sh)) for p, g, m, v, sh in entries)
+        if key == self.key:
+            return
+        assert len(entries) <= self.capacity
+        if self.key is not None and not torch.cuda.is_current_stream_capturing():
+            torch.cuda.current_stream().synchronize()  # an earlier upload may still be reading `pinned`
+        C.memset(self.host, 0, C.sizeof(self.host))
         for i, (p, g, m, v, sh) in enumerate(entries):
             t = self.host[i]
             t.p, t.g, t.m, t.v = _p(p), _p(g), _p(m), _p(v)
@@ -278,12 +337,9 @@ class AdamTable:
                 t.p_bf16 = _p(sh)
                 t.shadow_cols = p.shape[-1]
                 t.shadow_ld = sh.shape[-1]
-        raw = bytes(self.host)
-        # pinned staging so the upload is a capturable async memcpy (CUDA-graph safe)
-        self.pinned = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone().pin_memory()
-        self.dev = torch.empty(len(raw), dtype=torch.uint8, device=rt.device())
-        self.dev.copy_(self.pinned, non_blocking=True)
-        self.key = tuple((_p(p), _p(g), _p(m), _p(v), _p(sh)) for p, g, m, v, sh in entries)
+        C.memmove(self.pinned.ptr, self.host, C.sizeof(self.host))
+        self.pinned.to_device(self.dev)  # async memcpy node: safe under graph capture
+        self.n, self.key, self.keep = len(entries), key, entries
 
 
 def adam_step(table: AdamTable, lr, b1, omb1, b2, omb2, c1, c2, eps):

@@ -37,7 +37,9 @@ class Adam:
         self.beta2 = beta2
         self.eps = eps
         self.timestep = 1
-        self._table = None
+        self._table = None          # the table eager steps recycle
+        self._tables = {}           # pointer-key -> table (captured graphs keep theirs forever)
+        self._spare_tables = []
         self.init()
 
     def init(self):
@@ -79,11 +81,9 @@ class Adam:
             g = p.gradient if p.gradient.is_contiguous() else p.gradient.contiguous()
             shadow = lyr._shadows.get(name) if rt.is_bf16() else None
             entries.append((p.data, g, state.momentum.data, state.velocity.data, shadow))
-        key = tuple((rt.ptr(a), rt.ptr(b), rt.ptr(c), rt.ptr(d), rt.ptr(e)) for a, b, c, d, e in entries)
-        if self._table is None or self._table.key != key:
-            self._table = ops.AdamTable(entries)
+        table = self._table_for(entries)
         t = self.timestep
-        ops.adam_step(self._table, _f32(self.learning_rate), _f32(self.beta1), _f32(1 - self.beta1),
+        ops.adam_step(table,_f32(self.learning_rate), _f32(self.beta1), _f32(1 - self.beta1),
                       _f32(self.beta2), _f32(1 - self.beta2), _f32(1 - self.beta1**t), _f32(1 - self.beta2**t),
                       _f32(self.eps))
         for lyr, name, state in todo:
@@ -91,6 +91,40 @@ class Adam:
             p = lyr.parameters[name]
             setattr(lyr, name, type(p)(data=p.data, gradient=None, shard_axis=p.shard_axis))
             lyr.parameters[name] = getattr(lyr, name)
+
+    def _table_for(self, entries):
+        """Pointer table for this set of buffers.  Eager steps recycle one table; every CUDA-graph
+        capture takes its own pre-allocated table, which is never touched again (a replayed graph
+        reads it)."""
+        import torch
+
+        key = tuple((rt.ptr(a), rt.ptr(b), rt.ptr(c), rt.ptr(d), rt.ptr(e)) for a, b, c, d, e in entries)
+        cap = max(len(entries), self._count_parameters())
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            while len(self._spare_tables) < 3:  # pinned allocations are illegal during capture
+                self._spare_tables.append(ops.AdamTable(cap))
+        table = self._tables.get(key)
+        if table is not None:
+            return table
+        if capturing:
+            if not self._spare_tables:
+                raise RuntimeError("Adam: run one eager step before capturing more CUDA graphs")
+            table = self._spare_tables.pop()
+        else:
+            if self._table is None or self._table.capacity < len(entries):
+                self._table = ops.AdamTable(cap)
+            table = self._table
+            self._tables = {k: v for k, v in self._tables.items() if v is not table}
+        table.fill(entries)
+        self._tables[key] = table
+        return table
+
+    def _count_parameters(self) -> int:
+        def walk(params):
+            return sum(1 if isinstance(v, AdamParams) else walk(v) for v in params.values())
+
+        return walk(self.parameters)
 
     def scatter(self, params: dict = None):
         if params is None:

@@ -5,7 +5,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from . import runtime as rt
 from .nn import softmax_cross_entropy
 from .nn.core import _host_to_device
@@ -41,42 +41,67 @@ class GraphedTrainStep:
     `step(x, y)` takes HOST uint16 arrays: they are copied into pinned staging buffers, the graph
     (H2D copies + every kernel of the step + the D2H copy of the mean loss) is launched once, and
     the loss is read back.  Launch-bound inner loops (~150 kernels per step at the Shakespeare
-    shape) become a single graph launch.
+    shape) become a single graph launch.  `step_resident()` replays the same step on token
+    buffers that already live in HBM (no host copies in the graph).
     """
 
     def __init__(self, transformer, optimizer, batch: int, seq_len: int, warmup: int = 2):
         rt.require_gpu("GraphedTrainStep")
         self.transformer, self.optimizer = transformer, optimizer
-        self.x_host = torch.empty((batch, seq_len), dtype=torch.uint16).pin_memory()
-        self.y_host = torch.empty((batch, seq_len), dtype=torch.uint16).pin_memory()
-        self.loss_host = torch.zeros((1,), dtype=torch.float32).pin_memory()
+        n = batch * seq_len * 2
+        self._x_pin, self._y_pin, self._loss_pin = ops.PinnedBuffer(n), ops.PinnedBuffer(n), ops.PinnedBuffer(4)
+        self.x_host = self._x_pin.view(np.uint16, (batch, seq_len))
+        self.y_host = self._y_pin.view(np.uint16, (batch, seq_len))
+        self.loss_host = self._loss_pin.view(np.float32, (1,))
+        self.h2d_bytes_per_step, self.d2h_bytes_per_step = 2 * n, 4
         self.x_dev = rt.empty((batch, seq_len), torch.uint16)
         self.y_dev = rt.empty((batch, seq_len), torch.uint16)
-        self.graph = None
+        self.loss_dev = rt.zeros((1,))
+        self.graph = None            # H2D + step + D2H
+        self.graph_resident = None   # step only, tokens already in x_dev / y_dev
+        self.launches_per_step = None
         self.warmup = warmup
         self._eager_steps = 0
         self.stream = torch.cuda.Stream()
 
-    def _body(self):
-        self.x_dev.copy_(self.x_host, non_blocking=True)
-        self.y_dev.copy_(self.y_host, non_blocking=True)
+    # -- bodies -----------------------------------------------------------------------------------
+    def _compute(self):
         loss = train_step_device(self.transformer, self.optimizer, self.x_dev, self.y_dev)
-        self.loss_host.copy_(loss, non_blocking=True)
+        ops.check(_lib.load().npt_memcpy_async(self.loss_dev.data_ptr(), loss.data_ptr(), 4, 3, rt.stream()),
+                  "npt_memcpy_async")
 
-    def step_async(self, x: np.ndarray, y: np.ndarray) -> None:
-        self.x_host.numpy()[...] = x
-        self.y_host.numpy()[...] = y
+    def _body(self):
+        self._x_pin.to_device(self.x_dev)
+        self._y_pin.to_device(self.y_dev)
+        self._compute()
+        self._loss_pin.from_device(self.loss_dev)
+
+    def _warm(self, body) -> bool:
         if self._eager_steps < self.warmup:
             with torch.cuda.stream(self.stream):
-                self._body()
+                body()
             self._eager_steps += 1
+            return True
+        return False
+
+    def _capture(self, body):
+        self.stream.synchronize()
+        lib = _lib.load()
+        before = lib.npt_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.stream):
+            body()
+        self.launches_per_step = int(lib.npt_launch_count() - before)
+        return g
+
+    # -- host-buffer API (what a user calls) ----------------------------------------------------------
+    def step_async(self, x: np.ndarray, y: np.ndarray) -> None:
+        self.x_host[...] = x
+        self.y_host[...] = y
+        if self._warm(self._body):
             return
         if self.graph is None:
-            self.stream.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self.stream):
-                self._body()
-            self.graph = g
+            self.graph = self._capture(self._body)
         with torch.cuda.stream(self.stream):
             self.graph.replay()
 
@@ -84,3 +109,20 @@ class GraphedTrainStep:
         self.step_async(x, y)
         self.stream.synchronize()
         return float(self.loss_host[0])
+
+    # -- device-resident API (tokens already in HBM) -----------------------------------------------------
+    def load_resident(self, x_dev: torch.Tensor, y_dev: torch.Tensor) -> None:
+        """Device-to-device copy of a resident batch into the graph's token buffers (stream-ordered)."""
+        lib = _lib.load()
+        with torch.cuda.stream(self.stream):
+            n = self.x_dev.numel() * 2
+            ops.check(lib.npt_memcpy_async(self.x_dev.data_ptr(), x_dev.data_ptr(), n, 3, rt.stream()), "memcpy")
+            ops.check(lib.npt_memcpy_async(self.y_dev.data_ptr(), y_dev.data_ptr(), n, 3, rt.stream()), "memcpy")
+
+    def step_resident_async(self) -> None:
+        if self._warm(self._compute):
+            return
+        if self.graph_resident is None:
+            self.graph_resident = self._capture(self._compute)
+        with torch.cuda.stream(self.stream):
+            self.graph_resident.replay()

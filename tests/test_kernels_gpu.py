@@ -305,7 +305,8 @@ def test_adam_bit_exact(golden_layers):
     f = lambda x: float(np.float32(x))
     for i in range(3):
         g = dev(G[f"adam/g{i}"])
-        table = ops.AdamTable([(p, g, m, v, None)])
+        table = ops.AdamTable(1)
+        table.fill([(p, g, m, v, None)])
         ops.adam_step(table, f(1e-3), f(0.9), f(1 - 0.9), f(0.99), f(1 - 0.99), f(1 - 0.9), f(1 - 0.99), f(1e-7))
         np.testing.assert_array_equal(host(p), G[f"adam/p{i + 1}"])
     np.testing.assert_array_equal(host(m), G["adam/m"])
@@ -325,7 +326,8 @@ def test_adam_multi_tensor_bit_exact_vs_oracle():
         pt = dev(p)
         sh = ops.cast_bf16(pt, pad_cols=True) if p.ndim == 2 else None
         entries.append((pt, dev(g), dev(m), dev(v), sh))
-    table = ops.AdamTable(entries)
+    table = ops.AdamTable(len(entries))
+    table.fill(entries)
     ops.adam_step(table, f(1e-4), f(0.9), f(1 - 0.9), f(0.99), f(1 - 0.99), f(1 - 0.9), f(1 - 0.99), f(1e-7))
     for (pt, _, mt, vt, sh), p, g, m, v in zip(entries, ps, gs, ms, vs):
         p2, m2, v2 = O.adam_update(p, g, m, v, 1e-4, 0.9, 0.99)
