@@ -1,0 +1,91 @@
+"""One rank (one GPU) of the multi-GPU parity test: the tiny model trained for 3 steps under
+tp x dp, compared with the golden vectors recorded from the reference run as tp*dp processes."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+
+import numpitron_b200 as nb  # noqa: E402
+from numpitron_b200 import distributed as npdist  # noqa: E402
+from numpitron_b200.nn import Transformer, softmax_cross_entropy  # noqa: E402
+from numpitron_b200.optimizer import Adam  # noqa: E402
+from numpitron_b200.runtime import to_numpy  # noqa: E402
+from numpitron_b200.train import GraphedTrainStep  # noqa: E402
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+TINY = dict(d_model=32, n_heads=4, n_layers=2, vocab_size=17, seq_len=16)
+
+
+def load(name):
+    with np.load(GOLDEN / name) as z:
+        return {k: z[k] for k in z.files}
+
+
+def close(got, want, rtol, what):
+    got, want = to_numpy(got), np.asarray(want)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=rtol * np.abs(want).max(), err_msg=what)
+
+
+def main(tp, dp, precision):
+    rank = int(os.environ["RANK"])
+    nb.set_precision(precision)
+    npdist.init(tp_size=tp, dp_size=dp)
+    rtol = 2e-5 if precision == "fp32" else 3e-2
+    W, G = load(f"tiny_tp{tp}_dp{dp}.npz"), load("layers_tp1.npz")
+    model = Transformer(**TINY, rng=np.random.default_rng(42))
+    opt = Adam(model, 1e-4, 0.9, 0.99)
+    model.scatter()
+    opt.scatter()
+    for i in range(3):
+        x, y = G[f"tiny/x{i}"], G[f"tiny/y{i}"]
+        if dp > 1:
+            x = np.ascontiguousarray(np.array_split(x, dp, axis=0)[npdist.data_parallel_rank()])
+            y = np.ascontiguousarray(np.array_split(y, dp, axis=0)[npdist.data_parallel_rank()])
+        logits = model(x)
+        loss, d = softmax_cross_entropy(logits, y)
+        model.backward(d)
+        if i == 0:
+            close(logits, W[f"rank{rank}/logits0"], rtol, "logits0")
+            close(model.input_embedding.embedding.gradient, W[f"rank{rank}/dE0"], 10 * rtol, "dE0")
+        opt.step()
+        close(loss, W[f"rank{rank}/loss{i}"], rtol, f"loss{i}")
+    close(model.input_embedding.embedding.data, W[f"rank{rank}/E_final"], rtol, "E_final")
+    # Adam's update is lr*g/(|g|+eps): with bf16 operands a noisy tiny gradient moves a weight by up
+    # to lr per step, so after 3 steps weights are compared to within 3.5*lr absolute in bf16 mode.
+    w_got = to_numpy(model.block_0.mlp.column_linear.weight.data)
+    w_want = W[f"rank{rank}/w1_final_block0"]
+    if precision == "fp32":
+        close(w_got, w_want, rtol, "w1_final")
+    else:
+        assert np.abs(w_got - w_want).max() <= 3.5e-4, np.abs(w_got - w_want).max()
+
+    # the CUDA-graph replay (NCCL all-reduces captured inside) gives the eager numbers
+    model2 = Transformer(**TINY, rng=np.random.default_rng(42))
+    opt2 = Adam(model2, 1e-4, 0.9, 0.99)
+    model2.scatter()
+    opt2.scatter()
+    lb = 4 // dp
+    g = GraphedTrainStep(model2, opt2, lb, 16, warmup=1)
+    for i in range(3):
+        x, y = G[f"tiny/x{i}"], G[f"tiny/y{i}"]
+        if dp > 1:
+            x = np.ascontiguousarray(np.array_split(x, dp, axis=0)[npdist.data_parallel_rank()])
+            y = np.ascontiguousarray(np.array_split(y, dp, axis=0)[npdist.data_parallel_rank()])
+        got = g.step(x, y)
+        want = W[f"rank{rank}/loss{i}"].mean()
+        assert abs(got - want) <= rtol * abs(want), (i, got, want)
+    assert g.graph is not None
+    close(model2.input_embedding.embedding.data, W[f"rank{rank}/E_final"], rtol, "graph E_final")
+    torch.cuda.synchronize()
+    print(f"rank {rank} ok", flush=True)
+    sys.stdout.flush()
+    os._exit(0)  # skip NCCL teardown (it can block behind captured graphs); the work is verified
+
+
+if __name__ == "__main__":
+    main(int(sys.argv[1]), int(sys.argv[2]), sys.argv[3])
