@@ -1,7 +1,8 @@
 // bf16 tensor-core GEMM for sm_100a: TMA -> 128B-swizzled shared memory -> tcgen05.mma with the
-// fp32 accumulator in TMEM -> tcgen05.ld epilogue (alpha / bias / ReLU / ReLU-mask, fp32 and/or
-// bf16 stores).  Serves every dense contraction of the training step in the bf16 throughput mode
-// (nn/linear.py:44,55,60; nn/attention.py:48,52,81-92; nn/embedding.py:92,99,102).
+// fp32 accumulator in TMEM -> tcgen05.ld epilogue (alpha / bias / ReLU / ReLU-mask) -> swizzled
+// shared-memory staging -> TMA store (fp32 and/or bf16).  Serves every dense contraction of the
+// training step in the bf16 throughput mode (nn/linear.py:44,55,60; nn/attention.py:48,52,81-92;
+// nn/embedding.py:92,99,102).
 //
 // Layout support (no operand is ever transposed in memory):
 //   A K-major  (trans_a=0, stored M x K)   one TMA box {64 k, 128 m}
@@ -11,10 +12,12 @@
 // Batches ride in tensor-map dimensions 2 and 3 (inner / outer batch index), which is how the
 // per-head [q|k|v] column layout of the QKV projection is addressed in place.
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer (one elected lane),
-// warps 2-5 epilogue (one TMEM lane quarter each).  One 128 x BN output tile per CTA, two CTAs
-// per SM so one tile's epilogue overlaps the other's main loop.  Split-K partials go to a
-// workspace and are reduced in fixed order by gemm.cu (deterministic).
+// Persistent: one CTA per SM loops over 128 x BN output tiles (n fastest, so the A panel of a
+// row of tiles stays in L2).  6 warps: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
+// (one elected lane), warps 2-5 = epilogue (one TMEM lane quarter each).  The accumulator is
+// double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the main loop of
+// tile i+1.  Split-K partials go to a workspace (also by TMA store) and are reduced in fixed
+// order by gemm.cu (deterministic).
 #include <cuda.h>
 
 #include "gemm_common.cuh"
@@ -24,6 +27,7 @@ namespace npt {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;  // bf16 elements = 128 bytes = one swizzle row
 constexpr int TC_THREADS = 192;
+constexpr int TC_STAGES = 4;
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -33,6 +37,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -46,6 +53,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -55,6 +63,15 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -111,76 +128,112 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
          | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-template <int BN, int STAGES>
+template <int BN>
 struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int PIPE_BYTES = TC_STAGES * STAGE_BYTES;
+  // per epilogue warp: 2 x (32 rows x 128 B) fp32 staging + 2 x (32 rows x 64 B) bf16 staging
+  static constexpr int EPI_F32 = 32 * 128, EPI_BF16 = 32 * 64;
+  static constexpr int EPI_WARP_BYTES = 2 * EPI_F32 + 2 * EPI_BF16;
+  static constexpr int EPI_OFFSET = PIPE_BYTES;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + 4 * EPI_WARP_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * TC_STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(TC_THREADS)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-               int K, int batch, int splits, int kb_per_split, GemmEpilogue epi, float* __restrict__ partial) {
-  using L = TcSmem<BN, STAGES>;
+struct TcParams {
+  int M, N, K, batch, splits, kb_per_split;
+  int m_tiles, n_tiles, total_tiles;
+  int tma_store;  // 1: staged TMA-store epilogue; 0: direct register stores (unaligned outputs)
+  int raw;        // 1: split-K partial (no epilogue math), stored through map C as {N, M, batch, split}
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCb,
+               const TcParams p, const GemmEpilogue epi, float* __restrict__ partial) {
+  using L = TcSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + TC_STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bz = blockIdx.z;
-  const int b = bz / splits, split = bz - b * splits;
-  const int bo = b / epi.batch_inner, bi = b - bo * epi.batch_inner;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  const int kblocks = (K + TC_BK - 1) / TC_BK;
-  const int kb_begin = split * kb_per_split;
-  int kb_end = kb_begin + kb_per_split;
-  if (kb_end > kblocks) kb_end = kblocks;
-  const int nkb = kb_end - kb_begin;  // host guarantees nkb >= 1
+  const int kblocks = (p.K + TC_BK - 1) / TC_BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
+    if (p.tma_store) {
+      if (epi.C || p.raw) tma_prefetch_desc(&tmC);
+      if (epi.Cb && !p.raw) tma_prefetch_desc(&tmCb);
+    }
+    for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar + a, 1);
+      mbar_init(tmem_empty_bar + a, 4);  // one arrive per epilogue warp
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // tile -> (n_tile fastest, m_tile, z = batch*splits)
+  auto decode = [&](int t, int& m0, int& n0, int& b, int& split, int& bi, int& bo, int& kb_begin, int& nkb) {
+    const int nt = t % p.n_tiles;
+    const int r = t / p.n_tiles;
+    const int mt = r % p.m_tiles;
+    const int z = r / p.m_tiles;
+    b = z / p.splits;
+    split = z - b * p.splits;
+    bo = b / epi.batch_inner;
+    bi = b - bo * epi.batch_inner;
+    m0 = mt * TC_BM;
+    n0 = nt * BN;
+    kb_begin = split * p.kb_per_split;
+    int kb_end = kb_begin + p.kb_per_split;
+    if (kb_end > kblocks) kb_end = kblocks;
+    nkb = kb_end - kb_begin;  // host guarantees >= 1
+  };
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, it = i / STAGES;
-        mbar_wait(empty_bar + s, (it & 1) ^ 1);
-        mbar_expect_tx(full_bar + s, L::STAGE_BYTES);
-        uint8_t* sa = smem + s * L::STAGE_BYTES;
-        uint8_t* sb = sa + L::A_BYTES;
-        const int k0 = (kb_begin + i) * TC_BK;
-        if (A_MN) {
-          tma_load_4d(&tmA, full_bar + s, sa, m0, k0, bi, bo);
-          tma_load_4d(&tmA, full_bar + s, sa + 64 * TC_BK * 2, m0 + 64, k0, bi, bo);
-        } else {
-          tma_load_4d(&tmA, full_bar + s, sa, k0, m0, bi, bo);
-        }
-        if (B_MN) {
+      uint32_t it = 0;  // running k-block counter across tiles
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int m0, n0, b, split, bi, bo, kb_begin, nkb;
+        decode(t, m0, n0, b, split, bi, bo, kb_begin, nkb);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % TC_STAGES;
+          mbar_wait(empty_bar + s, ((it / TC_STAGES) & 1) ^ 1);
+          mbar_expect_tx(full_bar + s, L::STAGE_BYTES);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          const int k0 = (kb_begin + i) * TC_BK;
+          if (A_MN) {
+            tma_load_4d(&tmA, full_bar + s, sa, m0, k0, bi, bo);
+            tma_load_4d(&tmA, full_bar + s, sa + 64 * TC_BK * 2, m0 + 64, k0, bi, bo);
+          } else {
+            tma_load_4d(&tmA, full_bar + s, sa, k0, m0, bi, bo);
+          }
+          if (B_MN) {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c)
-            tma_load_4d(&tmB, full_bar + s, sb + c * 64 * TC_BK * 2, n0 + c * 64, k0, bi, bo);
-        } else {
-          tma_load_4d(&tmB, full_bar + s, sb, k0, n0, bi, bo);
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_4d(&tmB, full_bar + s, sb + c * 64 * TC_BK * 2, n0 + c * 64, k0, bi, bo);
+          } else {
+            tma_load_4d(&tmB, full_bar + s, sb, k0, n0, bi, bo);
+          }
         }
       }
     }
@@ -188,63 +241,166 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, it = i / STAGES;
-        mbar_wait(full_bar + s, it & 1);
+      uint32_t it = 0, tile_i = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_i) {
+        int m0, n0, b, split, bi, bo, kb_begin, nkb;
+        decode(t, m0, n0, b, split, bi, bo, kb_begin, nkb);
+        const uint32_t acc = tile_i & 1;
+        mbar_wait(tmem_empty_bar + acc, ((tile_i >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t sb = sa + L::A_BYTES;
-        // K-major: 16 k = 32 B inside the 128 B swizzle row.  MN-major: 16 k = two 8-k groups = 2048 B.
-        const uint64_t da = A_MN ? make_smem_desc(sa, 64 * TC_BK * 2, 1024) : make_smem_desc(sa, 16, 1024);
-        const uint64_t db = B_MN ? make_smem_desc(sb, 64 * TC_BK * 2, 1024) : make_smem_desc(sb, 16, 1024);
-        constexpr uint32_t adv_a = (A_MN ? 2048 : 32) >> 4, adv_b = (B_MN ? 2048 : 32) >> 4;
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % TC_STAGES;
+          mbar_wait(full_bar + s, (it / TC_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+          // K-major: 16 k = 32 B inside the 128 B swizzle row.  MN-major: 16 k = two 8-k groups = 2048 B.
+          const uint64_t da = A_MN ? make_smem_desc(sa, 64 * TC_BK * 2, 1024) : make_smem_desc(sa, 16, 1024);
+          const uint64_t db = B_MN ? make_smem_desc(sb, 64 * TC_BK * 2, 1024) : make_smem_desc(sb, 16, 1024);
+          constexpr uint32_t adv_a = (A_MN ? 2048 : 32) >> 4, adv_b = (B_MN ? 2048 : 32) >> 4;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)
-          umma_bf16(tmem_base, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc, (i > 0 || k > 0) ? 1u : 0u);
-        umma_commit(empty_bar + s);  // frees this smem stage once the MMAs above retire
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(d_tmem, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc, (i > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar + s);  // frees this smem stage once the MMAs above retire
+        }
+        umma_commit(tmem_full_bar + acc);  // accumulator complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
     const int quarter = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int m = m0 + quarter * 32 + lane;
+    uint8_t* stage_base = smem + L::EPI_OFFSET + (warp - 2) * L::EPI_WARP_BYTES;
+    const bool want_f32 = p.raw || epi.C != nullptr;
+    const bool want_bf16 = !p.raw && epi.Cb != nullptr;
+    const bool masked = !p.raw && epi.mask != nullptr;
+    uint32_t tile_i = 0, store_i = 0;  // store_i counts committed TMA-store groups (staging buffer parity)
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_i) {
+      int m0, n0, b, split, bi, bo, kb_begin, nkb;
+      decode(t, m0, n0, b, split, bi, bo, kb_begin, nkb);
+      const uint32_t acc = tile_i & 1;
+      mbar_wait(tmem_full_bar + acc, (tile_i >> 1) & 1);
+      tc_fence_after();
+      const int mrow0 = m0 + quarter * 32;  // first row of this warp's 32-row band
+      const int m = mrow0 + lane;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
-      tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (m < M && nb < N) {
-        if (splits > 1) {
-          float* prow = partial + (((int64_t)split * batch + b) * M + m) * N;
-          if ((N & 3) == 0) {
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+        }
+        const int nb = n0 + c * 32;
+        if (!p.tma_store) {
+          // ---- direct stores (outputs whose pitch/base TMA cannot address, e.g. N = 65) ----
+          if (m < p.M && nb < p.N) {
+            if (p.raw) {
+              float* prow = partial + (((int64_t)split * p.batch + b) * p.M + m) * p.N;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (nb + j < N)
-                *reinterpret_cast<float4*>(prow + nb + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          } else {
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) prow[nb + j] = __uint_as_float(r[j]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < N) prow[nb + j] = __uint_as_float(r[j]);
+              for (int j = 0; j < 32; j += 4)
+                epi_store4(epi, b, m, nb + j, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+            }
           }
-        } else {
+          continue;
+        }
+        if (mrow0 >= p.M || nb >= p.N) continue;  // whole 32x32 block is outside (warp-uniform)
+        // ---- staged TMA-store epilogue ----
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            epi_store4(epi, b, m, nb + j, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (!p.raw) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= epi.alpha;
+          if (epi.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += (nb + j < p.N) ? __ldg(epi.bias + nb + j) : 0.f;
+          }
+          if (epi.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+        }
+        const uint32_t bufsel = store_i & 1;
+        ++store_i;
+        uint8_t* s32 = stage_base + bufsel * L::EPI_F32;
+        uint8_t* s16 = stage_base + 2 * L::EPI_F32 + bufsel * L::EPI_BF16;
+        // the TMA store that last read this buffer (two chunks ago) must have finished reading it
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        if (want_f32 || masked) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)  // SWIZZLE_128B: 16-byte chunk j of row r lands at chunk j ^ (r & 7)
+            *reinterpret_cast<float4*>(s32 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (masked) {
+          // second pass in a coalesced layout: lane -> (row = i*4 + lane/8, 16-byte chunk = lane%8)
+          __syncwarp();
+          const int bo_ = bo, bi_ = bi;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + (lane >> 3), ch = lane & 7;
+            float4* sp = reinterpret_cast<float4*>(s32 + row * 128 + ((ch ^ (row & 7)) << 4));
+            float4 x = *sp;
+            const int gm = mrow0 + row, gn = nb + ch * 4;
+            float mk[4] = {0.f, 0.f, 0.f, 0.f};
+            if (gm < p.M) {
+              const int64_t off = bo_ * epi.smo + bi_ * epi.smi + (int64_t)gm * epi.ldm + gn;
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (gn + e < p.N)
+                  mk[e] = epi.mask_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(epi.mask)[off + e])
+                                        : reinterpret_cast<const float*>(epi.mask)[off + e];
+            }
+            x.x = mk[0] > 0.f ? x.x : 0.f; x.y = mk[1] > 0.f ? x.y : 0.f;
+            x.z = mk[2] > 0.f ? x.z : 0.f; x.w = mk[3] > 0.f ? x.w : 0.f;
+            if (want_f32) *sp = x;
+            if (want_bf16) {  // SWIZZLE_64B: 16-byte chunk q of row r lands at chunk q ^ ((r >> 1) & 3)
+              uint2 u;
+              u.x = pack_bf16(x.x, x.y);
+              u.y = pack_bf16(x.z, x.w);
+              *reinterpret_cast<uint2*>(s16 + row * 64 + (((ch >> 1) ^ ((row >> 1) & 3)) << 4) + ((ch & 1) << 3)) = u;
+            }
+          }
+        } else if (want_bf16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16(v[8 * q], v[8 * q + 1]);
+            u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+            u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]);
+            u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+            *reinterpret_cast<uint4*>(s16 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = u;
+          }
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          if (p.raw) {
+            tma_store_4d(&tmC, s32, nb, mrow0, b, split);
+          } else {
+            if (want_f32) tma_store_4d(&tmC, s32, nb, mrow0, bi, bo);
+            if (want_bf16) tma_store_4d(&tmCb, s16, nb, mrow0, bi, bo);
+          }
+          tma_store_commit();
         }
       }
     }
+    if (lane == 0) tma_store_wait_all();  // global writes complete before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
@@ -265,24 +421,28 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 4-D bf16 tensor map: dims {inner (contiguous), rows, batch_inner, batch_outer}.
-static int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t ld, int64_t n_bi,
-                    int64_t s_bi, int64_t n_bo, int64_t s_bo, int box_inner, int box_rows) {
+// 4-D tensor map: dims {inner (contiguous), rows, batch_inner, batch_outer}; strides in elements.
+static int make_map(CUtensorMap* map, CUtensorMapDataType dt, int es, CUtensorMapSwizzle sw, const void* base,
+                    int64_t inner, int64_t rows, int64_t ld, int64_t n_bi, int64_t s_bi, int64_t n_bo, int64_t s_bo,
+                    int box_inner, int box_rows) {
   EncodeTiledFn enc = get_encode();
   NPT_REQUIRE(enc != nullptr, "gemm(tc): cuTensorMapEncodeTiled not available from the driver");
-  const int64_t es = 2;
   cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)n_bi, (cuuint64_t)n_bo};
   const int64_t natural = ((rows * ld * es + 15) / 16) * 16;
   cuuint64_t strides[3] = {(cuuint64_t)(ld * es), (cuuint64_t)(n_bi > 1 ? s_bi * es : natural),
                            (cuuint64_t)(n_bo > 1 ? s_bo * es : natural)};
   cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NPT_REQUIRE(r == CUDA_SUCCESS, "gemm(tc): cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld rows=%lld ld=%lld)",
               (int)r, (long long)inner, (long long)rows, (long long)ld);
   return 0;
+}
+static int make_map_bf16(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t ld, int64_t n_bi,
+                         int64_t s_bi, int64_t n_bo, int64_t s_bo, int box_inner, int box_rows) {
+  return make_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_128B, base, inner, rows, ld, n_bi, s_bi,
+                  n_bo, s_bo, box_inner, box_rows);
 }
 
 int gemm_tc_supported(const npt_gemm_args& a) {
@@ -301,9 +461,9 @@ int gemm_tc_splits(const npt_gemm_args& a) {
   const int bn = tc_bn(a);
   const int64_t tiles = cdiv(a.M, TC_BM) * cdiv(a.N, bn) * a.batch;
   const int64_t kblocks = cdiv(a.K, TC_BK);
-  const int64_t target = (int64_t)sm_count() * 2;
-  if (tiles >= target || kblocks < 8) return 1;
-  int64_t s = target / tiles;
+  const int64_t target = (int64_t)sm_count();
+  if (tiles * 2 > target || kblocks < 8) return 1;
+  int64_t s = (target + tiles - 1) / tiles;
   if (s > kblocks / 4) s = kblocks / 4;  // >= 4 k-blocks (256 k) per split
   if (s > 64) s = 64;
   if (s < 1) s = 1;
@@ -312,42 +472,76 @@ int gemm_tc_splits(const npt_gemm_args& a) {
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_tc(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, float* partial,
-                     const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
-  constexpr int STAGES = 3;
-  using L = TcSmem<BN, STAGES>;
-  auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
+static int launch_tc(const TcParams& p, const GemmEpilogue& epi, float* partial, const CUtensorMap& tmA,
+                     const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCb, cudaStream_t st) {
+  using L = TcSmem<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
     NPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  const int kblocks = (int)cdiv(a.K, TC_BK);
-  const int kps = (int)cdiv(kblocks, splits);
-  dim3 grid((unsigned)cdiv(a.N, BN), (unsigned)cdiv(a.M, TC_BM), (unsigned)(a.batch * splits));
-  kern<<<grid, TC_THREADS, L::TOTAL, st>>>(tmA, tmB, a.M, a.N, a.K, a.batch, splits, kps, epi, partial);
+  int grid = sm_count();
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  kern<<<grid, TC_THREADS, L::TOTAL, st>>>(tmA, tmB, tmC, tmCb, p, epi, partial);
   NPT_LAUNCH_CHECK();
   return 0;
 }
 
 int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, float* partial, cudaStream_t st) {
-  NPT_REQUIRE((int64_t)a.batch * splits <= 65535, "gemm(tc): batch*splits exceeds grid.z");
   const int bn = tc_bn(a);
   const int64_t n_bi = a.batch_inner, n_bo = cdiv(a.batch, a.batch_inner);
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC, tmCb;
+  memset(&tmC, 0, sizeof(tmC));
+  memset(&tmCb, 0, sizeof(tmCb));
   int rc;
-  if (a.trans_a) rc = make_map(&tmA, a.A, a.M, a.K, a.lda, n_bi, a.stride_a_inner, n_bo, a.stride_a_outer, 64, 64);
-  else           rc = make_map(&tmA, a.A, a.K, a.M, a.lda, n_bi, a.stride_a_inner, n_bo, a.stride_a_outer, 64, TC_BM);
+  if (a.trans_a) rc = make_map_bf16(&tmA, a.A, a.M, a.K, a.lda, n_bi, a.stride_a_inner, n_bo, a.stride_a_outer, 64, 64);
+  else           rc = make_map_bf16(&tmA, a.A, a.K, a.M, a.lda, n_bi, a.stride_a_inner, n_bo, a.stride_a_outer, 64, TC_BM);
   if (rc) return rc;
-  if (a.trans_b) rc = make_map(&tmB, a.B, a.K, a.N, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, bn);
-  else           rc = make_map(&tmB, a.B, a.N, a.K, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, 64);
+  if (a.trans_b) rc = make_map_bf16(&tmB, a.B, a.K, a.N, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, bn);
+  else           rc = make_map_bf16(&tmB, a.B, a.N, a.K, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, 64);
   if (rc) return rc;
+
+  TcParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.batch = a.batch; p.splits = splits;
+  const int kblocks = (int)cdiv(a.K, TC_BK);
+  p.kb_per_split = (int)cdiv(kblocks, splits);
+  p.m_tiles = (int)cdiv(a.M, TC_BM);
+  p.n_tiles = (int)cdiv(a.N, bn);
+  const int64_t total = (int64_t)p.m_tiles * p.n_tiles * a.batch * splits;
+  NPT_REQUIRE(total < ((int64_t)1 << 31), "gemm(tc): too many tiles");
+  p.total_tiles = (int)total;
+  p.raw = splits > 1;
+  // Can the outputs be written by TMA?  (16-byte aligned base, pitches and batch strides)
+  if (p.raw) {
+    p.tma_store = (a.N % 4 == 0) && aligned16(partial);
+    if (p.tma_store) {
+      rc = make_map(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B, partial, a.N, a.M, a.N, a.batch,
+                    (int64_t)a.M * a.N, splits, (int64_t)a.batch * a.M * a.N, 32, 32);
+      if (rc) return rc;
+    }
+  } else {
+    const bool c_ok = !a.C || (aligned16(a.C) && a.ldc % 4 == 0 && a.stride_c_outer % 4 == 0 && a.stride_c_inner % 4 == 0);
+    const bool cb_ok = !a.C_bf16 || (aligned16(a.C_bf16) && a.ldcb % 8 == 0 && a.stride_cb_outer % 8 == 0 &&
+                                     a.stride_cb_inner % 8 == 0);
+    p.tma_store = c_ok && cb_ok;
+    if (p.tma_store && a.C) {
+      rc = make_map(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B, a.C, a.N, a.M, a.ldc, n_bi,
+                    a.stride_c_inner, n_bo, a.stride_c_outer, 32, 32);
+      if (rc) return rc;
+    }
+    if (p.tma_store && a.C_bf16) {
+      rc = make_map(&tmCb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_64B, a.C_bf16, a.N, a.M, a.ldcb, n_bi,
+                    a.stride_cb_inner, n_bo, a.stride_cb_outer, 32, 32);
+      if (rc) return rc;
+    }
+  }
   const bool a_mn = a.trans_a != 0, b_mn = a.trans_b == 0;
-#define NPT_TC_CASE(BNV)                                                                          \
-  if (a_mn && b_mn) return launch_tc<BNV, true, true>(a, epi, splits, partial, tmA, tmB, st);     \
-  if (a_mn && !b_mn) return launch_tc<BNV, true, false>(a, epi, splits, partial, tmA, tmB, st);   \
-  if (!a_mn && b_mn) return launch_tc<BNV, false, true>(a, epi, splits, partial, tmA, tmB, st);   \
-  return launch_tc<BNV, false, false>(a, epi, splits, partial, tmA, tmB, st);
+#define NPT_TC_CASE(BNV)                                                                            \
+  if (a_mn && b_mn) return launch_tc<BNV, true, true>(p, epi, partial, tmA, tmB, tmC, tmCb, st);     \
+  if (a_mn && !b_mn) return launch_tc<BNV, true, false>(p, epi, partial, tmA, tmB, tmC, tmCb, st);   \
+  if (!a_mn && b_mn) return launch_tc<BNV, false, true>(p, epi, partial, tmA, tmB, tmC, tmCb, st);   \
+  return launch_tc<BNV, false, false>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
   if (bn == 64) { NPT_TC_CASE(64) }
   NPT_TC_CASE(128)
 #undef NPT_TC_CASE

@@ -105,6 +105,42 @@ def test_gemm_bf16_splitk_and_epilogue():
     assert run_gemm(1, 130, 72, 4096, True, False, bias=True) < 2e-5
 
 
+def test_gemm_bf16_persistent_many_tiles_and_fused_epilogues():
+    """Bench-size linear layers: > 148 tiles per launch (persistent loop, both TMEM accumulators),
+    bf16-only outputs, bias+ReLU, bf16 ReLU-mask — checked against an fp64 product on the GPU."""
+    rng = np.random.default_rng(9)
+    M, K, N = 16384, 384, 1536
+    x = bf16_round(rng.standard_normal((M, K)))
+    w = bf16_round(rng.standard_normal((K, N)) * 0.05)
+    bias = rng.standard_normal(N).astype(np.float32)
+    xt, wt = dev(x).bfloat16(), dev(w).bfloat16()
+    ref = torch.clamp(dev(x).double() @ dev(w).double() + dev(bias).double(), min=0)
+    yb = rt.empty((M, N), torch.bfloat16)
+    ops.gemm(xt, wt, M, N, K, lda=K, ldb=N, Cb_out=yb, ldcb=N, bias=dev(bias), relu=True, mode=1)   # bf16 only
+    torch.cuda.synchronize()
+    err = (yb.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 6e-3, err
+    y = rt.empty((M, N))
+    ops.gemm(xt, wt, M, N, K, lda=K, ldb=N, C_out=y, ldc=N, Cb_out=yb, ldcb=N, bias=dev(bias), relu=True, mode=1)
+    torch.cuda.synchronize()
+    assert (y.double() - ref).abs().max().item() / ref.abs().max().item() < 1e-5
+    np.testing.assert_array_equal(host(yb), bf16_round(host(y)))
+    # dX = (dY @ W2^T) * (hidden > 0) with the bf16 hidden tensor as mask, bf16 + fp32 outputs
+    dy = bf16_round(rng.standard_normal((M, K)))
+    w2 = bf16_round(rng.standard_normal((N, K)) * 0.05)            # stored (d_hidden, d_out) = (N, K)
+    dyt, w2t = dev(dy).bfloat16(), dev(w2).bfloat16()
+    dx, dxb = rt.empty((M, N)), rt.empty((M, N), torch.bfloat16)
+    ops.gemm(dyt, w2t, M, N, K, lda=K, ldb=K, trans_b=True, C_out=dx, ldc=N, Cb_out=dxb, ldcb=N, mask=yb, ldmask=N, mode=1)
+    torch.cuda.synchronize()
+    ref2 = (dev(dy).double() @ dev(w2).double().T) * (yb.double() > 0)
+    assert (dx.double() - ref2).abs().max().item() / ref2.abs().max().item() < 1e-5
+    np.testing.assert_array_equal(host(dxb), bf16_round(host(dx)))
+    dxb2 = rt.empty((M, N), torch.bfloat16)                          # masked, bf16-only output
+    ops.gemm(dyt, w2t, M, N, K, lda=K, ldb=K, trans_b=True, Cb_out=dxb2, ldcb=N, mask=yb, ldmask=N, mode=1)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(host(dxb2), host(dxb))
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_gemm_batched_head_layout(mode):
     """q@k^T and p@v addressed in place inside the (B,S,h,3,Dh) projection output (attention.py:43-52)."""
