@@ -89,7 +89,7 @@ int npt_cast_f32_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_ds
  *      `norm(sub(x)) + x`, nn/transformer_block.py:20-21).  mean/var (population) are saved.
  * bwd: dgamma = sum dy*xhat, dbeta = sum dy, dx = (g*dy - c1*xhat - c2) / sqrt(var)  — the
  *      final division uses std WITHOUT eps exactly as normalization.py:45-50 does.
- *      partial: workspace of npt_layernorm_bwd_workspace_bytes(rows,d) bytes.
+ *      partial: workspace of npt_layernorm_bwd_workspace_bytes(rows,d) bytes.  dx or dx_bf16 may be NULL.
  */
 int npt_layernorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual,
                       float* y, void* y_bf16, float* mean, float* var,
@@ -106,16 +106,17 @@ int npt_relu_bwd(const float* x, const float* dy, float* dx, void* dx_bf16, int6
 
 /* Column sum over rows: db = dy.sum(axis=(0,1)) — nn/linear.py:57-58.  Deterministic two-stage. */
 size_t npt_colsum_workspace_bytes(int64_t rows, int32_t cols);
-int npt_colsum(const float* x, int64_t ld, float* out, int64_t rows, int32_t cols,
+int npt_colsum(const void* x, int32_t x_is_bf16, int64_t ld, float* out, int64_t rows, int32_t cols,
                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- causal softmax over attention scores — nn/attention.py:48-51,87; nn/activation.py:6-31
  * fwd: P = softmax(where(j<=i, S/divisor, -inf)) row-wise over (rows_total = B*h*S) x S.
  * bwd: dS = where(j<=i, P*(dP - sum_j dP*P), 0) / divisor   (compact form of the Jacobian).
+ * Either output (fp32 / bf16) may be NULL; the backward reads P as fp32 or as the bf16 copy.
  */
 int npt_softmax_causal_fwd(const float* scores, float* p, void* p_bf16, int64_t n_mats, int32_t S,
                            float divisor, void* stream);
-int npt_softmax_causal_bwd(const float* p, const float* dp, float* ds, void* ds_bf16,
+int npt_softmax_causal_bwd(const void* p, int32_t p_is_bf16, const float* dp, float* ds, void* ds_bf16,
                            int64_t n_mats, int32_t S, float divisor, void* stream);
 
 /* ---- embeddings — nn/embedding.py:44-83,125-128 ---------------------------------------------

@@ -90,8 +90,10 @@ cast_bf16_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* _
 // Column sums, stage 1: block b sums rows [b*rpb, (b+1)*rpb) for a 32-column strip.
 // Threads are (32 columns) x (8 row lanes); coalesced 128 B reads per warp.
 __global__ void __launch_bounds__(256)
-colsum_stage1_kernel(const float* __restrict__ x, int64_t ld, float* __restrict__ partial,
+colsum_stage1_kernel(const void* __restrict__ xv, int x_is_bf16, int64_t ld, float* __restrict__ partial,
                      int64_t rows, int cols, int64_t rows_per_block) {
+  const float* x = reinterpret_cast<const float*>(xv);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xv);
   __shared__ float sm[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
@@ -100,7 +102,7 @@ colsum_stage1_kernel(const float* __restrict__ x, int64_t ld, float* __restrict_
   if (r1 > rows) r1 = rows;
   float acc = 0.f;
   if (col < cols)
-    for (int64_t r = r0 + ry; r < r1; r += 8) acc += x[r * ld + col];
+    for (int64_t r = r0 + ry; r < r1; r += 8) acc += x_is_bf16 ? __bfloat162float(xb[r * ld + col]) : x[r * ld + col];
   sm[ry][cx] = acc;
   __syncthreads();
   if (ry == 0 && col < cols) {
@@ -179,7 +181,7 @@ size_t npt_colsum_workspace_bytes(int64_t rows, int32_t cols) {
   return (size_t)colsum_parts(rows, cols) * (size_t)cols * sizeof(float);
 }
 
-int npt_colsum(const float* x, int64_t ld, float* out, int64_t rows, int32_t cols, void* workspace,
+int npt_colsum(const void* x, int32_t x_is_bf16, int64_t ld, float* out, int64_t rows, int32_t cols, void* workspace,
                size_t workspace_bytes, void* stream) {
   NPT_REQUIRE(rows > 0 && cols > 0 && ld >= cols, "colsum: bad shape");
   NPT_REQUIRE(workspace && workspace_bytes >= npt_colsum_workspace_bytes(rows, cols),
@@ -188,7 +190,7 @@ int npt_colsum(const float* x, int64_t ld, float* out, int64_t rows, int32_t col
   const int parts = colsum_parts(rows, cols);
   const int64_t rpb = cdiv(rows, parts);
   dim3 grid((unsigned)cdiv(cols, 32), (unsigned)parts);
-  colsum_stage1_kernel<<<grid, 256, 0, st>>>(x, ld, (float*)workspace, rows, cols, rpb);
+  colsum_stage1_kernel<<<grid, 256, 0, st>>>(x, x_is_bf16, ld, (float*)workspace, rows, cols, rpb);
   NPT_LAUNCH_CHECK();
   colsum_stage2_kernel<<<(unsigned)cdiv(cols, 256), 256, 0, st>>>((const float*)workspace, out, parts, cols);
   NPT_LAUNCH_CHECK();

@@ -27,7 +27,6 @@ namespace npt {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;  // bf16 elements = 128 bytes = one swizzle row
 constexpr int TC_THREADS = 192;
-constexpr int TC_STAGES = 4;
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,16 +129,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 
 template <int BN>
 struct TcSmem {
+  // smem budget: ~178 KB of pipeline stages next to 48 KB of epilogue staging
+  static constexpr int STAGES = BN >= 256 ? 3 : BN >= 192 ? 4 : BN >= 128 ? 5 : 6;
+  static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;  // power of two >= 2*BN
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int PIPE_BYTES = TC_STAGES * STAGE_BYTES;
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   // per epilogue warp: 2 x (32 rows x 128 B) fp32 staging + 2 x (32 rows x 64 B) bf16 staging
   static constexpr int EPI_F32 = 32 * 128, EPI_BF16 = 32 * 64;
   static constexpr int EPI_WARP_BYTES = 2 * EPI_F32 + 2 * EPI_BF16;
   static constexpr int EPI_OFFSET = PIPE_BYTES;
   static constexpr int BAR_OFFSET = EPI_OFFSET + 4 * EPI_WARP_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * TC_STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
 struct TcParams {
@@ -155,6 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCb,
                const TcParams p, const GemmEpilogue epi, float* __restrict__ partial) {
   using L = TcSmem<BN>;
+  constexpr int TC_STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -183,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<L::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -279,12 +282,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int m0, n0, b, split, bi, bo, kb_begin, nkb;
       decode(t, m0, n0, b, split, bi, bo, kb_begin, nkb);
       const uint32_t acc = tile_i & 1;
-      mbar_wait(tmem_full_bar + acc, (tile_i >> 1) & 1);
-      tc_fence_after();
       const int mrow0 = m0 + quarter * 32;  // first row of this warp's 32-row band
       const int m = mrow0 + lane;
+      // ReLU-mask prefetch (bf16 mask, aligned, block fully inside the matrix): eight 8-byte loads per
+      // lane, issued back to back one chunk ahead of their use.  lane -> (row i*4 + lane/8, cols (lane%8)*4..+3).
+      uint2 mnext[8];
+      bool next_fast = false;
+      auto prefetch_mask = [&](int cc) {
+        const int nbm = n0 + cc * 32;
+        next_fast = epi.mask_bf16 && epi.mask_vec4 && (mrow0 + 32 <= p.M) && (nbm + 32 <= p.N);
+        if (next_fast) {
+          const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(epi.mask) + bo * epi.smo + bi * epi.smi +
+                                    (int64_t)(mrow0 + (lane >> 3)) * epi.ldm + nbm + (lane & 7) * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) mnext[i] = __ldg(reinterpret_cast<const uint2*>(mp + (int64_t)(i * 4) * epi.ldm));
+        }
+      };
+      if (masked && p.tma_store) prefetch_mask(0);
+      mbar_wait(tmem_full_bar + acc, (tile_i >> 1) & 1);
+      tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        // ReLU-mask bits for this warp's 32x32 block, fetched first so the global-load latency hides
+        // behind the TMEM load and the epilogue math: bit (4*i + e) <-> row i*4 + lane/8, col (lane%8)*4 + e.
+        uint32_t mbits = 0;
+        uint2 mraw[8];         // bf16 fast path: 4 mask values per 8-byte load
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mraw[i] = mnext[i];
+        const bool mask_fast = next_fast;
+        if (masked && p.tma_store) {
+          const int nbm = n0 + c * 32;
+          if (c + 1 < BN / 32) prefetch_mask(c + 1);  // next chunk's mask bits fly while this chunk is processed
+          if (mask_fast) {
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+              const int gm = mrow0 + i * 4 + (lane >> 3), gn = nbm + (lane & 7) * 4;
+              if (gm < p.M) {
+                const int64_t off = bo * epi.smo + bi * epi.smi + (int64_t)gm * epi.ldm + gn;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (gn + e < p.N) {
+                    const float mv = epi.mask_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(epi.mask)[off + e])
+                                                   : reinterpret_cast<const float*>(epi.mask)[off + e];
+                    mbits |= (mv > 0.f ? 1u : 0u) << (4 * i + e);
+                  }
+              }
+            }
+          }
+        }
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
         tmem_ld_wait();
@@ -342,26 +388,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         if (masked) {
+          if (mask_fast) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&mraw[i].x);
+              const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&mraw[i].y);
+              mbits |= ((__low2float(lo) > 0.f ? 1u : 0u) | (__high2float(lo) > 0.f ? 2u : 0u) |
+                        (__low2float(hi) > 0.f ? 4u : 0u) | (__high2float(hi) > 0.f ? 8u : 0u)) << (4 * i);
+            }
+          }
           // second pass in a coalesced layout: lane -> (row = i*4 + lane/8, 16-byte chunk = lane%8)
           __syncwarp();
-          const int bo_ = bo, bi_ = bi;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = i * 4 + (lane >> 3), ch = lane & 7;
             float4* sp = reinterpret_cast<float4*>(s32 + row * 128 + ((ch ^ (row & 7)) << 4));
             float4 x = *sp;
-            const int gm = mrow0 + row, gn = nb + ch * 4;
-            float mk[4] = {0.f, 0.f, 0.f, 0.f};
-            if (gm < p.M) {
-              const int64_t off = bo_ * epi.smo + bi_ * epi.smi + (int64_t)gm * epi.ldm + gn;
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (gn + e < p.N)
-                  mk[e] = epi.mask_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(epi.mask)[off + e])
-                                        : reinterpret_cast<const float*>(epi.mask)[off + e];
-            }
-            x.x = mk[0] > 0.f ? x.x : 0.f; x.y = mk[1] > 0.f ? x.y : 0.f;
-            x.z = mk[2] > 0.f ? x.z : 0.f; x.w = mk[3] > 0.f ? x.w : 0.f;
+            const uint32_t mb = mbits >> (4 * i);
+            x.x = (mb & 1u) ? x.x : 0.f; x.y = (mb & 2u) ? x.y : 0.f;
+            x.z = (mb & 4u) ? x.z : 0.f; x.w = (mb & 8u) ? x.w : 0.f;
             if (want_f32) *sp = x;
             if (want_bf16) {  // SWIZZLE_64B: 16-byte chunk q of row r lands at chunk q ^ ((r >> 1) & 3)
               uint2 u;
@@ -400,7 +445,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    tmem_dealloc<L::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -455,7 +500,20 @@ int gemm_tc_supported(const npt_gemm_args& a) {
   return 0;
 }
 
-static int tc_bn(const npt_gemm_args& a) { return a.N <= 64 ? 64 : 128; }
+// Tile width: minimise the operand bytes a row of tiles pulls through L2 (each tile loads 128 rows
+// of A and BN rows of B per k-block), ties broken towards less padded MMA work.
+static int tc_bn(const npt_gemm_args& a) {
+  if (a.N <= 64) return 64;
+  const int cand[3] = {128, 192, 256};
+  int best = 128;
+  int64_t best_cost = -1;
+  for (int i = 0; i < 3; ++i) {
+    const int64_t nt = cdiv(a.N, cand[i]);
+    const int64_t cost = nt * (cand[i] + 128) * 1024 + nt * cand[i];
+    if (best_cost < 0 || cost < best_cost) { best = cand[i]; best_cost = cost; }
+  }
+  return best;
+}
 
 int gemm_tc_splits(const npt_gemm_args& a) {
   const int bn = tc_bn(a);
@@ -543,6 +601,8 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
   if (!a_mn && b_mn) return launch_tc<BNV, false, true>(p, epi, partial, tmA, tmB, tmC, tmCb, st);   \
   return launch_tc<BNV, false, false>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
   if (bn == 64) { NPT_TC_CASE(64) }
+  if (bn == 192) { NPT_TC_CASE(192) }
+  if (bn == 256) { NPT_TC_CASE(256) }
   NPT_TC_CASE(128)
 #undef NPT_TC_CASE
 }

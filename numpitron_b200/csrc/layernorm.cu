@@ -165,7 +165,7 @@ ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
         o.y = __fdiv_rn(w[i].y - c1 * xh[i].y - c2, stdv);
         o.z = __fdiv_rn(w[i].z - c1 * xh[i].z - c2, stdv);
         o.w = __fdiv_rn(w[i].w - c1 * xh[i].w - c2, stdv);
-        st_stream(outr + c, o);
+        if (dx) st_stream(outr + c, o);
         if (dxb) st_bf16x4(dxb + row * d + (int64_t)c * 4, o);
       }
     }
@@ -221,7 +221,7 @@ ln_bwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
       const float xh = __fdiv_rn(xr[c] - mean, denom), w = gamma[c] * dr[c];
       const float o = __fdiv_rn(w - c1 * xh - c2, stdv);
-      dx[row * d + c] = o;
+      if (dx) dx[row * d + c] = o;
       if (dxb) dxb[row * d + c] = __float2bfloat16_rn(o);
     }
   }
@@ -310,6 +310,7 @@ int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, con
                       int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
                       void* stream) {
   NPT_REQUIRE(rows > 0 && d > 0, "layernorm_bwd: bad shape rows=%lld d=%d", (long long)rows, d);
+  NPT_REQUIRE(dx || dx_bf16, "layernorm_bwd: no output");
   NPT_REQUIRE(workspace && workspace_bytes >= npt_layernorm_bwd_workspace_bytes(rows, d),
               "layernorm_bwd: workspace too small (%zu < %zu)", workspace_bytes,
               npt_layernorm_bwd_workspace_bytes(rows, d));
@@ -317,7 +318,7 @@ int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, con
   float* partial = (float*)workspace;
   int nblocks;
   const bool vec = (d % 4 == 0) && d <= kLnMaxVec * 128 && aligned16(x) && aligned16(dy) &&
-                   aligned16(dx) && aligned16(gamma) && (!dx_bf16 || aligned8(dx_bf16)) &&
+                   (!dx || aligned16(dx)) && aligned16(gamma) && (!dx_bf16 || aligned8(dx_bf16)) &&
                    (size_t)kLnWarps * 2 * d * sizeof(float) <= 200 * 1024;
   if (vec) {
     nblocks = ln_bwd_blocks(rows);

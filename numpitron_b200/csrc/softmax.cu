@@ -21,7 +21,7 @@ softmax_causal_fwd_kernel(const float* __restrict__ scores, float* __restrict__ 
   if (row >= rows) return;
   const int i = (int)(row % S);  // query position inside its (S x S) matrix
   const float* sr = scores + row * S;
-  float* pr = p + row * S;
+  float* pr = p ? p + row * S : nullptr;
   __nv_bfloat16* br = pb ? pb + row * S : nullptr;
   const int valid = i + 1;
   if (NPL > 0) {
@@ -47,7 +47,7 @@ softmax_causal_fwd_kernel(const float* __restrict__ scores, float* __restrict__ 
       const int j = lane + k * 32;
       if (j < S) {
         const float o = __fdiv_rn(x[k], s);
-        pr[j] = o;
+        if (pr) pr[j] = o;
         if (br) br[j] = __float2bfloat16_rn(o);
       }
     }
@@ -60,7 +60,7 @@ softmax_causal_fwd_kernel(const float* __restrict__ scores, float* __restrict__ 
     s = warp_sum(s);
     for (int j = lane; j < S; j += 32) {
       const float o = (j < valid) ? __fdiv_rn(expf(__fdiv_rn(sr[j], divisor) - mx), s) : 0.f;
-      pr[j] = o;
+      if (pr) pr[j] = o;
       if (br) br[j] = __float2bfloat16_rn(o);
     }
   }
@@ -68,7 +68,7 @@ softmax_causal_fwd_kernel(const float* __restrict__ scores, float* __restrict__ 
 
 template <int NPL>
 __global__ void __launch_bounds__(kSmWarps * 32)
-softmax_causal_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp,
+softmax_causal_bwd_kernel(const void* __restrict__ pv, int p_is_bf16, const float* __restrict__ dp,
                           float* __restrict__ ds, __nv_bfloat16* __restrict__ dsb, int64_t rows, int S,
                           float divisor) {
   const int lane = threadIdx.x & 31;
@@ -76,9 +76,10 @@ softmax_causal_bwd_kernel(const float* __restrict__ p, const float* __restrict__
   if (row >= rows) return;
   const int i = (int)(row % S);
   const int valid = i + 1;
-  const float* pr = p + row * S;
+  const float* pr = reinterpret_cast<const float*>(pv) + row * S;
+  const __nv_bfloat16* prb = reinterpret_cast<const __nv_bfloat16*>(pv) + row * S;
   const float* dr = dp + row * S;
-  float* outr = ds + row * S;
+  float* outr = ds ? ds + row * S : nullptr;
   __nv_bfloat16* br = dsb ? dsb + row * S : nullptr;
   if (NPL > 0) {
     float a[NPL > 0 ? NPL : 1], g[NPL > 0 ? NPL : 1];
@@ -86,7 +87,7 @@ softmax_causal_bwd_kernel(const float* __restrict__ p, const float* __restrict__
 #pragma unroll
     for (int k = 0; k < NPL; ++k) {
       const int j = lane + k * 32;
-      a[k] = (j < valid) ? pr[j] : 0.f;
+      a[k] = (j < valid) ? (p_is_bf16 ? __bfloat162float(prb[j]) : pr[j]) : 0.f;
       g[k] = (j < valid) ? dr[j] : 0.f;
       dot += a[k] * g[k];
     }
@@ -96,17 +97,17 @@ softmax_causal_bwd_kernel(const float* __restrict__ p, const float* __restrict__
       const int j = lane + k * 32;
       if (j < S) {
         const float o = (j < valid) ? __fdiv_rn(a[k] * (g[k] - dot), divisor) : 0.f;
-        outr[j] = o;
+        if (outr) outr[j] = o;
         if (br) br[j] = __float2bfloat16_rn(o);
       }
     }
   } else {
     float dot = 0.f;
-    for (int j = lane; j < valid; j += 32) dot += pr[j] * dr[j];
+    for (int j = lane; j < valid; j += 32) dot += (p_is_bf16 ? __bfloat162float(prb[j]) : pr[j]) * dr[j];
     dot = warp_sum(dot);
     for (int j = lane; j < S; j += 32) {
-      const float o = (j < valid) ? __fdiv_rn(pr[j] * (dr[j] - dot), divisor) : 0.f;
-      outr[j] = o;
+      const float o = (j < valid) ? __fdiv_rn((p_is_bf16 ? __bfloat162float(prb[j]) : pr[j]) * (dr[j] - dot), divisor) : 0.f;
+      if (outr) outr[j] = o;
       if (br) br[j] = __float2bfloat16_rn(o);
     }
   }
@@ -132,6 +133,7 @@ extern "C" {
 int npt_softmax_causal_fwd(const float* scores, float* p, void* p_bf16, int64_t n_mats, int32_t S,
                            float divisor, void* stream) {
   NPT_REQUIRE(n_mats > 0 && S > 0, "softmax_causal_fwd: bad shape");
+  NPT_REQUIRE(p || p_bf16, "softmax_causal_fwd: no output");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = n_mats * S;
   NPT_SM_DISPATCH(softmax_causal_fwd_kernel, scores, p, (__nv_bfloat16*)p_bf16, rows, S, divisor);
@@ -139,12 +141,13 @@ int npt_softmax_causal_fwd(const float* scores, float* p, void* p_bf16, int64_t 
   return 0;
 }
 
-int npt_softmax_causal_bwd(const float* p, const float* dp, float* ds, void* ds_bf16, int64_t n_mats,
-                           int32_t S, float divisor, void* stream) {
+int npt_softmax_causal_bwd(const void* p, int32_t p_is_bf16, const float* dp, float* ds, void* ds_bf16,
+                           int64_t n_mats, int32_t S, float divisor, void* stream) {
   NPT_REQUIRE(n_mats > 0 && S > 0, "softmax_causal_bwd: bad shape");
+  NPT_REQUIRE(ds || ds_bf16, "softmax_causal_bwd: no output");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = n_mats * S;
-  NPT_SM_DISPATCH(softmax_causal_bwd_kernel, p, dp, ds, (__nv_bfloat16*)ds_bf16, rows, S, divisor);
+  NPT_SM_DISPATCH(softmax_causal_bwd_kernel, p, p_is_bf16, dp, ds, (__nv_bfloat16*)ds_bf16, rows, S, divisor);
   NPT_LAUNCH_CHECK();
   return 0;
 }

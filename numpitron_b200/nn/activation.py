@@ -26,7 +26,8 @@ class Softmax(Layer):
         self.add_setting("axis", axis)
 
     def forward(self, inputs, divisor: float = 1.0):
-        outputs = ops.softmax_causal_fwd(inputs, divisor, want_bf16=rt.is_bf16())
+        # bf16 mode: the probabilities only feed tensor-core GEMMs (and their own backward)
+        outputs = ops.softmax_causal_fwd(inputs, divisor, bf16_only=rt.is_bf16())
         self.ctx["outputs"] = outputs
         self.ctx["divisor"] = divisor
         return outputs
@@ -34,7 +35,7 @@ class Softmax(Layer):
     def backward(self, d_out):
         """P*(dP - sum dP*P) (masked, / divisor): the compact form of activation.py:22-31."""
         outputs = self.ctx.pop("outputs")
-        return ops.softmax_causal_bwd(outputs, d_out, self.ctx.pop("divisor"), want_bf16=rt.is_bf16())
+        return ops.softmax_causal_bwd(outputs, d_out, self.ctx.pop("divisor"), bf16_only=rt.is_bf16())
 
 
 class ReLU(Layer):

@@ -5,10 +5,13 @@ per head as [q_h | k_h | v_h]; the score scale is 1/sqrt(d_model) (FULL model wi
 head count is n_heads // tp_size with no divisibility check.  Heads are never transposed or
 copied: every product is a strided-batched GEMM that addresses the (B,S,h,3,Dh) projection
 output in place and writes straight into the merged (B,S,h*Dh) / (B,S,h,3,Dh) layouts.
+In bf16 mode q/k/v, P, dS and the merged head outputs only feed tensor-core GEMMs and are kept
+in bf16 alone; scores and dP (softmax inputs) stay fp32.
 """
 from __future__ import annotations
 
 import numpy as np
+import torch
 
 from .. import distributed as npdist
 from .. import ops
@@ -16,6 +19,8 @@ from .. import runtime as rt
 from .activation import Softmax
 from .linear import Linear
 from .model import Model
+
+_BF16 = torch.bfloat16
 
 
 class Attention(Model):
@@ -33,25 +38,31 @@ class Attention(Model):
 
     @staticmethod
     def _operand(t):
-        """(tensor, row pitch) of an activation in the precision the GEMM runs in."""
-        if rt.is_bf16():
-            sh = rt.bf16_of(t) if hasattr(t, "_npt_bf16") else ops.cast_bf16(t, pad_cols=True)
+        """The tensor a GEMM reads: itself (fp32 mode / already bf16) or its bf16 copy."""
+        if not rt.is_bf16() or t.dtype == _BF16:
+            return t
+        sh = getattr(t, "_npt_bf16", None)
+        if sh is None:
+            sh = ops.cast_bf16(t, pad_cols=True)
             rt.attach_bf16(t, sh)
-            return sh
-        return t
+        return sh
 
     def forward(self, inputs):
         batch_size, seq_len, d_model = inputs.shape
         h = self._local_heads()
-        qkv = self.qkv_projection.forward(inputs, want_bf16=True)          # (B,S,h*3*Dh)
+        bf16 = rt.is_bf16()
+        qkv = self.qkv_projection.forward(inputs, out="bf16")              # (B,S,h*3*Dh)
         ld = qkv.shape[-1]
         dh3 = ld // h
         dh = dh3 // 3
+        if bf16:
+            assert seq_len % 8 == 0 and dh % 8 == 0, "bf16 mode needs seq_len and head_dim to be multiples of 8"
         divisor = float(np.float32(d_model**0.5))                           # attention.py:48
         nb = batch_size * h
         q_op = self._operand(qkv)
         head = (seq_len * ld, dh3)                                          # (batch, head) strides in qkv
         mat = (h * seq_len * seq_len, seq_len * seq_len)                    # ... in (B,h,S,S)
+        merged = (seq_len * h * dh, dh)                                     # ... in (B,S,h*Dh)
 
         scores = rt.empty((batch_size, h, seq_len, seq_len))               # q @ k^T
         ops.gemm(q_op, q_op, seq_len, seq_len, dh, lda=ld, ldb=ld, trans_b=True, a_off=0, b_off=dh,
@@ -60,15 +71,12 @@ class Attention(Model):
         attention_weights = self.softmax.forward(scores, divisor=divisor)   # scale, mask, softmax
         p_op = self._operand(attention_weights)
 
-        attention = rt.empty((batch_size, seq_len, h * dh))                 # p @ v, heads merged in place
-        att_b = rt.empty((batch_size, seq_len, h * dh), attention_dtype()) if rt.is_bf16() else None
-        merged = (seq_len * h * dh, dh)
+        att = None if bf16 else rt.empty((batch_size, seq_len, h * dh))     # p @ v, heads merged in place
+        att_b = rt.empty((batch_size, seq_len, h * dh), _BF16) if bf16 else None
         ops.gemm(p_op, q_op, seq_len, dh, seq_len, lda=seq_len, ldb=ld, b_off=2 * dh, a_strides=mat,
-                 b_strides=head, C_out=attention, ldc=h * dh, c_strides=merged,
+                 b_strides=head, C_out=att, ldc=h * dh, c_strides=merged,
                  Cb_out=att_b, ldcb=h * dh, cb_strides=merged, batch=nb, batch_inner=h)
-        if att_b is not None:
-            rt.attach_bf16(attention, att_b)
-        outputs = self.out_projection.forward(attention)
+        outputs = self.out_projection.forward(att_b if bf16 else att)
 
         self.ctx |= {"qkv": qkv, "attention_weights": attention_weights, "shape": (batch_size, seq_len, h, dh)}
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
@@ -79,16 +87,17 @@ class Attention(Model):
         batch_size, seq_len, h, dh = self.ctx.pop("shape")
         qkv = self.ctx.pop("qkv")
         p = self.ctx.pop("attention_weights")
+        bf16 = rt.is_bf16()
         ld = h * 3 * dh
         nb = batch_size * h
         head = (seq_len * ld, 3 * dh)
         mat = (h * seq_len * seq_len, seq_len * seq_len)
         merged = (seq_len * h * dh, dh)
 
-        d_att = self.out_projection.backward(d_out, want_bf16=True)         # (B,S,h*Dh)
+        d_att = self.out_projection.backward(d_out, out="bf16")             # (B,S,h*Dh)
         qkv_op, p_op, datt_op = self._operand(qkv), self._operand(p), self._operand(d_att)
-        d_qkv = rt.empty((batch_size, seq_len, ld))
-        d_qkv_b = rt.empty((batch_size, seq_len, ld), attention_dtype()) if rt.is_bf16() else None
+        d_qkv = None if bf16 else rt.empty((batch_size, seq_len, ld))
+        d_qkv_b = rt.empty((batch_size, seq_len, ld), _BF16) if bf16 else None
 
         def into_qkv(col):
             return dict(C_out=d_qkv, ldc=ld, c_off=col, c_strides=head,
@@ -102,7 +111,6 @@ class Attention(Model):
         ops.gemm(datt_op, qkv_op, seq_len, seq_len, dh, lda=h * dh, ldb=ld, trans_b=True, b_off=2 * dh,
                  a_strides=merged, b_strides=head, C_out=d_p, ldc=seq_len, c_strides=mat, batch=nb, batch_inner=h)
         # dS = softmax backward, masked, / sqrt(d_model)                     (attention.py:86-87)
-        self.softmax.ctx["outputs"] = p
         d_s = self.softmax.backward(d_p)
         ds_op = self._operand(d_s)
         # dQ = dS @ K ; dK = dS^T @ Q                                        (attention.py:89-92)
@@ -110,15 +118,7 @@ class Attention(Model):
                  batch=nb, batch_inner=h, **into_qkv(0))
         ops.gemm(ds_op, qkv_op, seq_len, dh, seq_len, lda=seq_len, ldb=ld, trans_a=True, b_off=0, a_strides=mat,
                  b_strides=head, batch=nb, batch_inner=h, **into_qkv(dh))
-        if d_qkv_b is not None:
-            rt.attach_bf16(d_qkv, d_qkv_b)
-        d_in = self.qkv_projection.backward(d_qkv)
+        d_in = self.qkv_projection.backward(d_qkv_b if bf16 else d_qkv)
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
             npdist.all_reduce(d_in, group=npdist.tensor_parallel_group())
         return d_in
-
-
-def attention_dtype():
-    import torch
-
-    return torch.bfloat16

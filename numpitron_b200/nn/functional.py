@@ -1,8 +1,10 @@
 """GEMM-level helpers shared by Linear / MLP / Attention / OutputEmbedding.
 
 Each helper is one `npt_gemm` call (plus a bf16 cast of an operand when no shadow exists yet).
-fp32 mode -> the FFMA kernel on fp32 operands; bf16 mode -> the tcgen05 kernel on bf16 shadows
-with fp32 accumulation and fp32 outputs (bf16 operands only, fp32 residual stream).
+fp32 mode -> the FFMA kernel on fp32 operands; bf16 mode -> the tcgen05 kernel on bf16 operands
+with fp32 accumulation.  In bf16 mode the residual stream, everything LayerNorm / softmax /
+loss / Adam touch and all weight gradients stay fp32; tensors that only ever feed
+another GEMM (`out="bf16"`) are stored as bf16 alone, which halves their HBM/L2 traffic.
 """
 from __future__ import annotations
 
@@ -17,6 +19,8 @@ _BF16 = torch.bfloat16
 def _act(x: torch.Tensor):
     """(operand tensor, leading dimension) of an activation for the current precision."""
     if rt.is_bf16():
+        if x.dtype == _BF16:
+            return x, x.shape[-1]
         sh = getattr(x, "_npt_bf16", None)
         if sh is None:
             sh = ops.cast_bf16(x, pad_cols=True)
@@ -33,19 +37,34 @@ def _weight(layer, name: str):
     return p, p.stride(0)
 
 
-def linear_forward(x, layer, wname="weight", bias=None, relu=False, want_bf16=False):
+def _outputs(shape, out: str):
+    """(fp32 buffer or None, bf16 buffer or None) for out in {"f32", "bf16", "both"}."""
+    n = shape[-1]
+    if not rt.is_bf16() or n % 8 != 0:
+        return rt.empty(shape), None
+    y = rt.empty(shape) if out in ("f32", "both") else None
+    yb = rt.empty(shape, _BF16) if out in ("bf16", "both") else None
+    return y, yb
+
+
+def _result(y, yb):
+    if y is None:
+        return yb
+    if yb is not None:
+        rt.attach_bf16(y, yb)
+    return y
+
+
+def linear_forward(x, layer, wname="weight", bias=None, relu=False, out="f32"):
     """y = x @ W (+ b) (ReLU) — nn/linear.py:44-47.  x (..., d_in), W (d_in, d_out)."""
     W = getattr(layer, wname).data
     d_in, d_out = W.shape
     T = x.numel() // d_in
     A, lda = _act(x)
     B, ldb = _weight(layer, wname)
-    y = rt.empty((*x.shape[:-1], d_out))
-    yb = rt.empty((*x.shape[:-1], d_out), _BF16) if (want_bf16 and rt.is_bf16() and d_out % 8 == 0) else None
+    y, yb = _outputs((*x.shape[:-1], d_out), out)
     ops.gemm(A, B, T, d_out, d_in, lda=lda, ldb=ldb, C_out=y, ldc=d_out, Cb_out=yb, ldcb=d_out, bias=bias, relu=relu)
-    if yb is not None:
-        rt.attach_bf16(y, yb)
-    return y
+    return _result(y, yb)
 
 
 def linear_backward_weight(x, dy):
@@ -59,26 +78,23 @@ def linear_backward_weight(x, dy):
     return dW
 
 
-def linear_backward_input(dy, layer, wname="weight", mask=None, want_bf16=False):
+def linear_backward_input(dy, layer, wname="weight", mask=None, out="f32"):
     """dx = dy @ W^T (optionally * (mask > 0): the fused ReLU.backward) — nn/linear.py:60."""
     W = getattr(layer, wname).data
     d_in, d_out = W.shape
     T = dy.numel() // d_out
     A, lda = _act(dy)
     B, ldb = _weight(layer, wname)
-    dx = rt.empty((*dy.shape[:-1], d_in))
-    dxb = rt.empty((*dy.shape[:-1], d_in), _BF16) if (want_bf16 and rt.is_bf16() and d_in % 8 == 0) else None
+    dx, dxb = _outputs((*dy.shape[:-1], d_in), out)
     mk, ldm = (None, 0)
     if mask is not None:
         mk, ldm = mask, mask.shape[-1]
     ops.gemm(A, B, T, d_in, d_out, lda=lda, ldb=ldb, trans_b=True, C_out=dx, ldc=d_in, Cb_out=dxb, ldcb=d_in,
              mask=mk, ldmask=ldm)
-    if dxb is not None:
-        rt.attach_bf16(dx, dxb)
-    return dx
+    return _result(dx, dxb)
 
 
 def bias_grad(dy):
-    """db = dy.sum(axis=(0,1)) — nn/linear.py:57-58."""
+    """db = dy.sum(axis=(0,1)) — nn/linear.py:57-58 (reads fp32 or bf16)."""
     n = dy.shape[-1]
     return ops.colsum(dy.numel() // n, n, dy)

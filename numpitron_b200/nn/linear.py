@@ -19,18 +19,19 @@ class Linear(Layer):
         if self.use_bias:
             self.add_parameter("bias", weight_init_fn(bias_init, **kwargs)((d_out,)), bias_shard_axis)
 
-    # MLP fuses ReLU into this layer's epilogues through the two keyword hooks.
-    def forward(self, inputs, relu: bool = False, want_bf16: bool = False):
+    # `relu`, `mask` and `out` are the hooks MLP / Attention use to fuse ReLU into this layer's GEMM
+    # epilogues and to keep GEMM-to-GEMM tensors in bf16 only (bf16 mode).
+    def forward(self, inputs, relu: bool = False, out: str = "f32"):
         """outputs = inputs @ W (+ b) — one GEMM with the bias (and ReLU) in its epilogue."""
         bias = self.bias.data if self.use_bias else None
-        outputs = F.linear_forward(inputs, self, "weight", bias=bias, relu=relu, want_bf16=want_bf16)
+        outputs = F.linear_forward(inputs, self, "weight", bias=bias, relu=relu, out=out)
         self.ctx["inputs"] = inputs
         return outputs
 
-    def backward(self, d_out, mask=None, want_bf16: bool = False):
+    def backward(self, d_out, mask=None, out: str = "f32"):
         """dW = x^T dy (replaces, never accumulates), db = sum dy, returns dx = dy W^T."""
         inputs = self.ctx.pop("inputs")
         self.update_parameter("weight", gradient=F.linear_backward_weight(inputs, d_out))
         if self.use_bias:
             self.update_parameter("bias", gradient=F.bias_grad(d_out))
-        return F.linear_backward_input(d_out, self, "weight", mask=mask, want_bf16=want_bf16)
+        return F.linear_backward_input(d_out, self, "weight", mask=mask, out=out)

@@ -3,7 +3,6 @@ Drop-in for the reference's nn/mlp.py; the ReLU lives in the GEMM epilogues."""
 from __future__ import annotations
 
 from .. import distributed as npdist
-from .. import runtime as rt
 from .activation import ReLU
 from .linear import Linear
 from .model import Model
@@ -21,8 +20,8 @@ class MLP(Model):
 
     def forward(self, inputs):
         # max(0, x@W1+b1) in one GEMM epilogue; the post-ReLU tensor doubles as the backward mask
-        # because relu(a) > 0  <=>  a > 0.
-        hidden = self.column_linear.forward(inputs, relu=True, want_bf16=True)
+        # because relu(a) > 0  <=>  a > 0.  It only feeds GEMMs, so bf16 mode keeps it in bf16 alone.
+        hidden = self.column_linear.forward(inputs, relu=True, out="bf16")
         outputs = self.row_linear.forward(hidden)
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
             npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
@@ -30,8 +29,7 @@ class MLP(Model):
 
     def backward(self, d_out):
         hidden = self.row_linear.ctx["inputs"]
-        mask = rt.bf16_of(hidden) if rt.is_bf16() and hasattr(hidden, "_npt_bf16") else hidden
-        d_out = self.row_linear.backward(d_out, mask=mask, want_bf16=True)  # (dy@W2^T) * (a>0)
+        d_out = self.row_linear.backward(d_out, mask=hidden, out="bf16")  # (dy@W2^T) * (a>0)
         d_out = self.column_linear.backward(d_out)
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
             npdist.all_reduce(d_out, group=npdist.tensor_parallel_group())

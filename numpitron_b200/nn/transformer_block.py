@@ -25,6 +25,6 @@ class TransformerBlock(Model):
 
     def backward(self, d_out):
         # The residual gradient is dropped, exactly as the reference does (Q2).
-        d_out = self.mlp.backward(self.norm2.backward(d_out))
-        d_out = self.attention.backward(self.norm1.backward(d_out))
+        d_out = self.mlp.backward(self.norm2.backward(d_out, gemm_only=True))
+        d_out = self.attention.backward(self.norm1.backward(d_out, gemm_only=True))
         return d_out

@@ -102,17 +102,20 @@ def layernorm_fwd(x, gamma, beta, eps, residual=None, want_bf16=False):
     return y, mean, var
 
 
-def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False):
+def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False, bf16_only=False):
+    """Returns (dx, dgamma, dbeta); with bf16_only dx is a bf16 tensor (it only feeds GEMMs)."""
     lib = _lib_()
     d = x.shape[-1]
     rows = x.numel() // d
-    dx = rt.empty(x.shape)
-    dxb = rt.empty(x.shape, _BF16) if want_bf16 else None
+    dx = None if bf16_only else rt.empty(x.shape)
+    dxb = rt.empty(x.shape, _BF16) if (want_bf16 or bf16_only) else None
     dgamma, dbeta = rt.empty((d,)), rt.empty((d,))
     need = lib.npt_layernorm_bwd_workspace_bytes(rows, d)
     ws = rt.workspace(need)
     check(lib.npt_layernorm_bwd(_p(x), _p(gamma), _p(mean), _p(var), _p(dy), _p(dx), _p(dxb), _p(dgamma), _p(dbeta),
                                 rows, d, eps, ws.data_ptr(), ws.numel(), rt.stream()), "npt_layernorm_bwd")
+    if bf16_only:
+        return dxb, dgamma, dbeta
     if dxb is not None:
         rt.attach_bf16(dx, dxb)
     return dx, dgamma, dbeta
@@ -145,30 +148,37 @@ def colsum(x2d_rows: int, cols: int, x: torch.Tensor, ld: int | None = None) -> 
     out = rt.empty((cols,))
     need = lib.npt_colsum_workspace_bytes(x2d_rows, cols)
     ws = rt.workspace(need)
-    check(lib.npt_colsum(_p(x), ld, _p(out), x2d_rows, cols, ws.data_ptr(), ws.numel(), rt.stream()), "npt_colsum")
+    check(lib.npt_colsum(_p(x), int(x.dtype == _BF16), ld, _p(out), x2d_rows, cols, ws.data_ptr(), ws.numel(),
+                         rt.stream()), "npt_colsum")
     return out
 
 
 # ---- causal softmax ----------------------------------------------------------------------------------
-def softmax_causal_fwd(scores, divisor, want_bf16=False):
+def softmax_causal_fwd(scores, divisor, want_bf16=False, bf16_only=False):
     lib = _lib_()
     S = scores.shape[-1]
     n_mats = scores.numel() // (S * S)
-    p = rt.empty(scores.shape)
-    pb = rt.empty(scores.shape, _BF16) if want_bf16 else None
+    p = None if bf16_only else rt.empty(scores.shape)
+    pb = rt.empty(scores.shape, _BF16) if (want_bf16 or bf16_only) else None
     check(lib.npt_softmax_causal_fwd(_p(scores), _p(p), _p(pb), n_mats, S, divisor, rt.stream()), "npt_softmax_causal_fwd")
+    if bf16_only:
+        return pb
     if pb is not None:
         rt.attach_bf16(p, pb)
     return p
 
 
-def softmax_causal_bwd(p, dp, divisor, want_bf16=False):
+def softmax_causal_bwd(p, dp, divisor, want_bf16=False, bf16_only=False):
+    """p may be the fp32 probabilities or their bf16 copy."""
     lib = _lib_()
     S = p.shape[-1]
     n_mats = p.numel() // (S * S)
-    ds = rt.empty(p.shape)
-    dsb = rt.empty(p.shape, _BF16) if want_bf16 else None
-    check(lib.npt_softmax_causal_bwd(_p(p), _p(dp), _p(ds), _p(dsb), n_mats, S, divisor, rt.stream()), "npt_softmax_causal_bwd")
+    ds = None if bf16_only else rt.empty(p.shape)
+    dsb = rt.empty(p.shape, _BF16) if (want_bf16 or bf16_only) else None
+    check(lib.npt_softmax_causal_bwd(_p(p), int(p.dtype == _BF16), _p(dp), _p(ds), _p(dsb), n_mats, S, divisor,
+                                     rt.stream()), "npt_softmax_causal_bwd")
+    if bf16_only:
+        return dsb
     if dsb is not None:
         rt.attach_bf16(ds, dsb)
     return ds

@@ -92,7 +92,8 @@ def test_gemm_fp32_splitk_and_epilogue():
 
 
 @pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
-@pytest.mark.parametrize("shape", [(128, 128, 64), (128, 64, 64), (128, 128, 256), (256, 384, 384), (200, 72, 136)])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (128, 64, 64), (128, 128, 256), (256, 384, 384), (200, 72, 136),
+                                   (384, 1536, 192), (300, 520, 72), (128, 1152, 64)])
 def test_gemm_bf16_tcgen05(shape, ta, tb):
     # inputs are exactly representable in bf16 -> only fp32 accumulation-order error remains
     assert run_gemm(1, *shape, ta, tb) < 1e-5
