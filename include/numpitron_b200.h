@@ -119,6 +119,22 @@ int npt_softmax_causal_fwd(const float* scores, float* p, void* p_bf16, int64_t 
 int npt_softmax_causal_bwd(const void* p, int32_t p_is_bf16, const float* dp, float* ds, void* ds_bf16,
                            int64_t n_mats, int32_t S, float divisor, void* stream);
 
+/* ---- fused causal attention (bf16 mode; P never leaves the SM) --------------------------------------
+ * Replaces nn/attention.py:43-52 (forward) and :81-98 (backward) for head_dim 64 and S % 128 == 0;
+ * other shapes use npt_gemm + npt_softmax_causal_*.  qkv is the QKV projection output
+ * (B,S,h,3,Dh) bf16 exactly as attention.py:43-45 lays it out ([q_h|k_h|v_h] per head); `out` /
+ * `d_out` are the merged heads (B,S,h*Dh) bf16; lse is the per-row log-sum-exp (B,h,S) fp32 saved
+ * for the backward; dqkv (B,S,h,3,Dh) bf16 = concat([dq,dk,dv],-1) merged back (attention.py:94-98).
+ * divisor = sqrt(d_model) (attention.py:48).  Deterministic (no atomics).
+ */
+int npt_attention_supported(int32_t S, int32_t Dh);
+int npt_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int32_t B, int32_t S, int32_t h,
+                      int32_t Dh, float divisor, void* stream);
+size_t npt_attention_bwd_workspace_bytes(int32_t B, int32_t S, int32_t h);
+int npt_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse,
+                      void* dqkv_bf16, int32_t B, int32_t S, int32_t h, int32_t Dh, float divisor,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- embeddings — nn/embedding.py:44-83,125-128 ---------------------------------------------
  * gather: out[t,:] = (tok in [chunk_start,chunk_end) ? E[:, tok-chunk_start] : 0) (+ pos[t % S,:]).
  *         E is (d, ldE>=V_local) row-major as the reference stores it.  `masked`=0 reproduces the

@@ -68,6 +68,10 @@ _SIGNATURES = {
     "npt_colsum": (c_int, [_P, c_int32, c_int64, _P, c_int64, c_int32, _P, c_size_t, _P]),
     "npt_softmax_causal_fwd": (c_int, [_P, _P, _P, c_int64, c_int32, c_float, _P]),
     "npt_softmax_causal_bwd": (c_int, [_P, c_int32, _P, _P, _P, c_int64, c_int32, c_float, _P]),
+    "npt_attention_supported": (c_int, [c_int32, c_int32]),
+    "npt_attention_fwd": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P]),
+    "npt_attention_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "npt_attention_bwd": (c_int, [_P, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, c_size_t, _P]),
     "npt_embedding_gather": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, _P]),
     "npt_add_pos": (c_int, [_P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
     "npt_embedding_scatter_add_workspace_bytes": (c_size_t, [c_int64, c_int32]),

@@ -1,0 +1,603 @@
+// Fused causal attention for sm_100a (bf16 mode): forward and backward without ever writing the
+// (B,h,S,S) score / probability matrices to HBM.  Replaces, for head_dim 64 and S % 128 == 0,
+//   forward : q@k^T / sqrt(d_model) -> causal mask -> softmax -> p@v        nn/attention.py:43-52
+//   backward: dV = p^T@dO, dP = dO@v^T, softmax backward, mask, scale,
+//             dQ = dS@k, dK = dS^T@q, concat([dq,dk,dv])                      nn/attention.py:81-98
+// operating directly on the (B,S,h,3,Dh) QKV-projection layout ([q_h|k_h|v_h] per head, Q4) and
+// the merged (B,S,h*Dh) head output.  The score scale is the caller's `divisor` (= sqrt(d_model),
+// NOT sqrt(head_dim): Q3).
+//
+// All three kernels share one shape: warp 0 = TMA producer, warp 1 = tcgen05 MMA issuer, warps 2-5
+// = one thread per query row (TMEM lane) doing the softmax arithmetic.  128x128 score tiles live in
+// TMEM; P / dS go through 128B-swizzled shared memory as the A operand of the second GEMM — read
+// K-major (P@V, dS@K) or MN-major (P^T@dO, dS^T@Q) from the same bytes; Q / dO / K / V tiles are
+// likewise read K-major or MN-major from the same TMA box.
+//   fwd : CTA = (b, head, 128 queries); loops over key tiles 0..diag (online softmax, fp32 running
+//         max / sum, O accumulated in registers); writes O (bf16) and the row log-sum-exp.
+//   dkv : CTA = (b, head, 128 keys); loops over query tiles diag..last; dK, dV accumulate in TMEM.
+//   dq  : CTA = (b, head, 128 queries); loops over key tiles 0..diag; dQ accumulates in TMEM.
+// No atomics: every output element has exactly one writer and a fixed summation order.
+#include "tc_ptx.cuh"
+
+namespace npt {
+using namespace tc;
+
+constexpr int AT_THREADS = 192;
+constexpr int AT_TILE = 128 * 64 * 2;  // one {64 x 128} bf16 TMA box = 16 KB
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) { return pack_bf16(a, b); }
+
+// Write 32 consecutive bf16 values (cols c*32 .. c*32+31 of a 128-wide row) of `row` into a
+// [2 halves][128 rows][128 B] swizzled tile (half = 64 columns).
+__device__ __forceinline__ void store_row_chunk(uint8_t* tile, int row, int c, const float (&v)[32]) {
+  uint8_t* base = tile + (c >> 1) * 16384;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack2(v[8 * q], v[8 * q + 1]);
+    u.y = pack2(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack2(v[8 * q + 4], v[8 * q + 5]);
+    u.w = pack2(v[8 * q + 6], v[8 * q + 7]);
+    *reinterpret_cast<uint4*>(base + swz128(row, (c & 1) * 4 + q)) = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+struct AttnFwdSmem {
+  static constexpr int Q = 0, K = AT_TILE, V = 3 * AT_TILE, P = 5 * AT_TILE, BAR = 7 * AT_TILE;
+  static constexpr int TOTAL = BAR + 16 * 8 + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out,
+                float* __restrict__ lse, int B, int S, int h, float inv_div) {
+  constexpr int DH = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdSmem::BAR);
+  uint64_t *q_full = bars, *k_full = bars + 1, *v_full = bars + 3, *kv_empty = bars + 5, *s_full = bars + 7,
+           *s_empty = bars + 8, *p_full = bars + 9, *pv_done = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqt = S / 128;
+  const int qt = nqt - 1 - (int)(blockIdx.x % nqt);  // heavy (late) query tiles first
+  const int bh = blockIdx.x / nqt;
+  const int b = bh / h, hh = bh - b * h;
+  const int n_kv = qt + 1;
+  const int col_q = hh * 3 * DH, col_k = col_q + DH, col_v = col_q + 2 * DH;
+  const int row0 = b * S;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(kv_empty + s, 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, AT_TILE);
+      tma_load_4d(&tmQKV, q_full, smem + AttnFwdSmem::Q, col_q, row0 + qt * 128, 0, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(kv_empty + st, ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(k_full + st, AT_TILE);
+        tma_load_4d(&tmQKV, k_full + st, smem + AttnFwdSmem::K + st * AT_TILE, col_k, row0 + j * 128, 0, 0);
+        mbar_expect_tx(v_full + st, AT_TILE);
+        tma_load_4d(&tmQKV, v_full + st, smem + AttnFwdSmem::V + st * AT_TILE, col_v, row0 + j * 128, 0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(128, false, false);  // S = Q K^T : both K-major
+      constexpr uint32_t idesc_o = make_idesc(DH, false, true);    // O = P V   : P K-major, V MN-major
+      const uint32_t sq = smem_u32(smem + AttnFwdSmem::Q), sp = smem_u32(smem + AttnFwdSmem::P);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1, ph = (j >> 1) & 1;
+        const uint32_t sk = smem_u32(smem + AttnFwdSmem::K + st * AT_TILE), sv = smem_u32(smem + AttnFwdSmem::V + st * AT_TILE);
+        mbar_wait(k_full + st, ph);
+        if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+        fence_after();
+        const uint64_t dq = make_smem_desc(sq, 16, 1024), dk = make_smem_desc(sk, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0);
+        umma_commit(s_full);
+        mbar_wait(v_full + st, ph);
+        mbar_wait(p_full, j & 1);
+        fence_after();
+        const uint64_t dv = make_smem_desc(sv, 16384, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // 128 keys = 8 x 16
+          const uint64_t dp = make_smem_desc(sp + (k >> 2) * 16384, 16, 1024) + (uint64_t)((k & 3) * 2);
+          umma_bf16(tmem_O, dp, dv + (uint64_t)(k * 128), idesc_o, k > 0);
+        }
+        umma_commit(pv_done);
+        umma_commit(kv_empty + st);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    uint8_t* sP = smem + AttnFwdSmem::P;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const bool diag = (j == qt);
+      mbar_wait(s_full, j & 1);
+      fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_S + lane_addr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t)
+          if (!diag || c * 32 + t <= row) mx = fmaxf(mx, __uint_as_float(r[t]) * inv_div);
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = (j == 0) ? 0.f : __expf(m_run - m_new);
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_S + lane_addr + c * 32, r);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const bool ok = !diag || c * 32 + t <= row;
+          p[t] = ok ? __expf(__uint_as_float(r[t]) * inv_div - m_new) : 0.f;
+          sum += p[t];
+        }
+        store_row_chunk(sP, row, c, p);
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      fence_before();          // TMEM reads of S are complete
+      fence_proxy_async();     // P writes visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
+      mbar_wait(pv_done, j & 1);
+      fence_after();
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_O + lane_addr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) o[c * 32 + t] = o[c * 32 + t] * alpha + __uint_as_float(r[t]);
+      }
+    }
+    const float inv_l = 1.0f / l_run;
+    const int64_t q_glob = (int64_t)row0 + qt * 128 + row;
+    __nv_bfloat16* orow = out + (q_glob * h + hh) * DH;
+#pragma unroll
+    for (int q = 0; q < DH / 8; ++q) {
+      uint4 u;
+      u.x = pack2(o[8 * q] * inv_l, o[8 * q + 1] * inv_l);
+      u.y = pack2(o[8 * q + 2] * inv_l, o[8 * q + 3] * inv_l);
+      u.z = pack2(o[8 * q + 4] * inv_l, o[8 * q + 5] * inv_l);
+      u.w = pack2(o[8 * q + 6] * inv_l, o[8 * q + 7] * inv_l);
+      *reinterpret_cast<uint4*>(orow + 8 * q) = u;
+    }
+    lse[((int64_t)b * h + hh) * S + qt * 128 + row] = m_run + __logf(l_run);
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: D[b,h,s] = sum_d dO*O   (8 lanes per row of 64)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                     float* __restrict__ D, int64_t rows /* B*S*h */, int S, int h) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int part = threadIdx.x & 7;
+  float acc = 0.f;
+  if (r < rows) {
+    const uint4 a = *reinterpret_cast<const uint4*>(o + r * 64 + part * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(d_o + r * 64 + part * 8);
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pg = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __bfloat1622float2(pa[i]), y = __bfloat1622float2(pg[i]);
+      acc += x.x * y.x + x.y * y.y;
+    }
+  }
+  acc += __shfl_xor_sync(kFull, acc, 1);
+  acc += __shfl_xor_sync(kFull, acc, 2);
+  acc += __shfl_xor_sync(kFull, acc, 4);
+  if (r < rows && part == 0) {
+    // row r = (b*S + s)*h + hh  ->  D[(b*h + hh)*S + s]
+    const int hh = (int)(r % h);
+    const int64_t bs = r / h;
+    const int64_t b = bs / S, s = bs - b * S;
+    D[(b * h + hh) * S + s] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, shared row arithmetic: p = exp(s/div - lse), dS = p*(dP - D)/div, both to smem tiles.
+// ------------------------------------------------------------------------------------------------
+template <bool WRITE_P>
+__device__ __forceinline__ void bwd_rows(uint32_t tmem_S, uint32_t tmem_dP, uint32_t lane_addr, int row, bool diag,
+                                         float lse_r, float D_r, float inv_div, uint8_t* sP, uint8_t* sdS) {
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t rs[32], rp[32];
+    tmem_ld_32x32(tmem_S + lane_addr + c * 32, rs);
+    tmem_ld_32x32(tmem_dP + lane_addr + c * 32, rp);
+    tmem_ld_wait();
+    float p[32], ds[32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const bool ok = !diag || c * 32 + t <= row;   // key index <= query index
+      p[t] = ok ? __expf(__uint_as_float(rs[t]) * inv_div - lse_r) : 0.f;
+      ds[t] = p[t] * (__uint_as_float(rp[t]) - D_r) * inv_div;
+    }
+    if (WRITE_P) store_row_chunk(sP, row, c, p);
+    store_row_chunk(sdS, row, c, ds);
+  }
+}
+
+__device__ __forceinline__ void store_acc_row(uint32_t taddr, __nv_bfloat16* dst) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 u;
+      u.x = pack2(__uint_as_float(r[8 * q]), __uint_as_float(r[8 * q + 1]));
+      u.y = pack2(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3]));
+      u.z = pack2(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5]));
+      u.w = pack2(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7]));
+      *reinterpret_cast<uint4*>(dst + c * 32 + 8 * q) = u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward dK / dV : CTA = (b, head, key tile j); loops over query tiles i = j .. nqt-1
+// ------------------------------------------------------------------------------------------------
+struct AttnDkvSmem {
+  static constexpr int K = 0, V = AT_TILE, Q = 2 * AT_TILE, DO = 4 * AT_TILE, P = 6 * AT_TILE, DS = 8 * AT_TILE,
+                       BAR = 10 * AT_TILE;
+  static constexpr int TOTAL = BAR + 16 * 8 + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                    const float* __restrict__ lse, const float* __restrict__ D, __nv_bfloat16* __restrict__ dqkv,
+                    int B, int S, int h, float inv_div) {
+  constexpr int DH = 64;
+  using L = AttnDkvSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+  uint64_t *kv_full = bars, *qdo_full = bars + 1, *qdo_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 6,
+           *pds_full = bars + 7, *acc_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqt = S / 128;
+  const int j = (int)(blockIdx.x % nqt);  // key tile; tile 0 has the most work and comes first
+  const int bh = blockIdx.x / nqt;
+  const int b = bh / h, hh = bh - b * h;
+  const int n_it = nqt - j;               // query tiles j .. nqt-1
+  const int col_q = hh * 3 * DH, col_k = col_q + DH, col_v = col_q + 2 * DH;
+  const int col_do = hh * DH;
+  const int row0 = b * S;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full + s, 1); mbar_init(qdo_empty + s, 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(pds_full, 4);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_S = tmem, tmem_dP = tmem + 128, tmem_dK = tmem + 256, tmem_dV = tmem + 320;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * AT_TILE);
+      tma_load_4d(&tmQKV, kv_full, smem + L::K, col_k, row0 + j * 128, 0, 0);
+      tma_load_4d(&tmQKV, kv_full, smem + L::V, col_v, row0 + j * 128, 0, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1, i = j + it;
+        mbar_wait(qdo_empty + st, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(qdo_full + st, 2 * AT_TILE);
+        tma_load_4d(&tmQKV, qdo_full + st, smem + L::Q + st * AT_TILE, col_q, row0 + i * 128, 0, 0);
+        tma_load_4d(&tmDO, qdo_full + st, smem + L::DO + st * AT_TILE, col_do, row0 + i * 128, 0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(128, false, false);  // S = Q K^T, dP = dO V^T
+      constexpr uint32_t idesc_a = make_idesc(DH, true, true);     // dV = P^T dO, dK = dS^T Q : both MN-major
+      const uint32_t sk = smem_u32(smem + L::K), sv = smem_u32(smem + L::V);
+      const uint32_t sp = smem_u32(smem + L::P), sds = smem_u32(smem + L::DS);
+      mbar_wait(kv_full, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1, ph = (it >> 1) & 1;
+        const uint32_t sq = smem_u32(smem + L::Q + st * AT_TILE), sdo = smem_u32(smem + L::DO + st * AT_TILE);
+        mbar_wait(qdo_full + st, ph);
+        if (it > 0) mbar_wait(s_empty, (it - 1) & 1);
+        fence_after();
+        const uint64_t dq = make_smem_desc(sq, 16, 1024), dk = make_smem_desc(sk, 16, 1024);
+        const uint64_t ddo = make_smem_desc(sdo, 16, 1024), dv = make_smem_desc(sv, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_dP, ddo + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), idesc_s, k > 0);
+        umma_commit(s_full);
+        mbar_wait(pds_full, it & 1);
+        fence_after();
+        // A = P^T / dS^T : MN-major (M = keys: two 64-key halves 16 KB apart; K = queries: 16 rows = 2048 B)
+        // B = dO / Q tile : MN-major (N = Dh, K = queries: 16 rows = 2048 B)
+        const uint64_t dpt = make_smem_desc(sp, 16384, 1024), ddst = make_smem_desc(sds, 16384, 1024);
+        const uint64_t dob = make_smem_desc(sdo, 16384, 1024), dqb = make_smem_desc(sq, 16384, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dV, dpt + (uint64_t)(k * 128), dob + (uint64_t)(k * 128), idesc_a, (it > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dK, ddst + (uint64_t)(k * 128), dqb + (uint64_t)(k * 128), idesc_a, (it > 0 || k > 0));
+        umma_commit(acc_done);
+        umma_commit(qdo_empty + st);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    for (int it = 0; it < n_it; ++it) {
+      const int i = j + it;
+      const int64_t stat = ((int64_t)b * h + hh) * S + i * 128 + row;
+      const float lse_r = lse[stat], D_r = D[stat];
+      mbar_wait(s_full, it & 1);
+      fence_after();
+      if (it > 0) mbar_wait(acc_done, (it - 1) & 1);  // P / dS tiles of the previous query tile are consumed
+      bwd_rows<true>(tmem_S, tmem_dP, lane_addr, row, it == 0, lse_r, D_r, inv_div, smem + L::P, smem + L::DS);
+      fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(pds_full); }
+    }
+    mbar_wait(acc_done, (n_it - 1) & 1);
+    fence_after();
+    // rows of dK / dV are KEYS of tile j
+    const int64_t k_glob = (int64_t)row0 + j * 128 + row;
+    __nv_bfloat16* base = dqkv + (k_glob * h + hh) * 3 * DH;
+    store_acc_row(tmem_dK + lane_addr, base + DH);
+    store_acc_row(tmem_dV + lane_addr, base + 2 * DH);
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward dQ : CTA = (b, head, query tile i); loops over key tiles j = 0 .. i
+// ------------------------------------------------------------------------------------------------
+struct AttnDqSmem {
+  static constexpr int Q = 0, DO = AT_TILE, K = 2 * AT_TILE, V = 4 * AT_TILE, DS = 6 * AT_TILE, BAR = 8 * AT_TILE;
+  static constexpr int TOTAL = BAR + 16 * 8 + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                   const float* __restrict__ lse, const float* __restrict__ D, __nv_bfloat16* __restrict__ dqkv,
+                   int B, int S, int h, float inv_div) {
+  constexpr int DH = 64;
+  using L = AttnDqSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+  uint64_t *qdo_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 6,
+           *ds_full = bars + 7, *acc_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqt = S / 128;
+  const int i = nqt - 1 - (int)(blockIdx.x % nqt);
+  const int bh = blockIdx.x / nqt;
+  const int b = bh / h, hh = bh - b * h;
+  const int n_kv = i + 1;
+  const int col_q = hh * 3 * DH, col_k = col_q + DH, col_v = col_q + 2 * DH;
+  const int col_do = hh * DH;
+  const int row0 = b * S;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(qdo_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(ds_full, 4);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_S = tmem, tmem_dP = tmem + 128, tmem_dQ = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(qdo_full, 2 * AT_TILE);
+      tma_load_4d(&tmQKV, qdo_full, smem + L::Q, col_q, row0 + i * 128, 0, 0);
+      tma_load_4d(&tmDO, qdo_full, smem + L::DO, col_do, row0 + i * 128, 0, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(kv_empty + st, ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(kv_full + st, 2 * AT_TILE);
+        tma_load_4d(&tmQKV, kv_full + st, smem + L::K + st * AT_TILE, col_k, row0 + j * 128, 0, 0);
+        tma_load_4d(&tmQKV, kv_full + st, smem + L::V + st * AT_TILE, col_v, row0 + j * 128, 0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(128, false, false);
+      constexpr uint32_t idesc_q = make_idesc(DH, false, true);  // dQ = dS K : dS K-major, K tile MN-major
+      const uint32_t sq = smem_u32(smem + L::Q), sdo = smem_u32(smem + L::DO), sds = smem_u32(smem + L::DS);
+      mbar_wait(qdo_full, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1, ph = (j >> 1) & 1;
+        const uint32_t sk = smem_u32(smem + L::K + st * AT_TILE), sv = smem_u32(smem + L::V + st * AT_TILE);
+        mbar_wait(kv_full + st, ph);
+        if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+        fence_after();
+        const uint64_t dq = make_smem_desc(sq, 16, 1024), dk = make_smem_desc(sk, 16, 1024);
+        const uint64_t ddo = make_smem_desc(sdo, 16, 1024), dv = make_smem_desc(sv, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_dP, ddo + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), idesc_s, k > 0);
+        umma_commit(s_full);
+        mbar_wait(ds_full, j & 1);
+        fence_after();
+        const uint64_t dkb = make_smem_desc(sk, 16384, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t dds = make_smem_desc(sds + (k >> 2) * 16384, 16, 1024) + (uint64_t)((k & 3) * 2);
+          umma_bf16(tmem_dQ, dds, dkb + (uint64_t)(k * 128), idesc_q, (j > 0 || k > 0));
+        }
+        umma_commit(acc_done);
+        umma_commit(kv_empty + st);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int64_t stat = ((int64_t)b * h + hh) * S + i * 128 + row;
+    const float lse_r = lse[stat], D_r = D[stat];
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      fence_after();
+      if (j > 0) mbar_wait(acc_done, (j - 1) & 1);  // previous dS tile consumed
+      bwd_rows<false>(tmem_S, tmem_dP, lane_addr, row, j == i, lse_r, D_r, inv_div, nullptr, smem + L::DS);
+      fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(ds_full); }
+    }
+    mbar_wait(acc_done, (n_kv - 1) & 1);
+    fence_after();
+    const int64_t q_glob = (int64_t)row0 + i * 128 + row;
+    store_acc_row(tmem_dQ + lane_addr, dqkv + (q_glob * h + hh) * 3 * DH);
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+static int check_shape(const char* who, int B, int S, int h, int Dh) {
+  NPT_REQUIRE(B > 0 && h > 0, "%s: bad shape", who);
+  NPT_REQUIRE(Dh == 64, "%s: fused attention supports head_dim 64 only (got %d); use the GEMM + softmax path", who, Dh);
+  NPT_REQUIRE(S > 0 && S % 128 == 0, "%s: fused attention needs seq_len %% 128 == 0 (got %d)", who, S);
+  return 0;
+}
+
+}  // namespace npt
+
+using namespace npt;
+
+extern "C" {
+
+int npt_attention_supported(int32_t S, int32_t Dh) { return (Dh == 64 && S > 0 && S % 128 == 0) ? 1 : 0; }
+
+int npt_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int32_t B, int32_t S, int32_t h, int32_t Dh,
+                      float divisor, void* stream) {
+  if (int rc = check_shape("attention_fwd", B, S, h, Dh)) return rc;
+  NPT_REQUIRE(aligned16(qkv_bf16) && aligned16(out_bf16), "attention_fwd: buffers must be 16-byte aligned");
+  CUtensorMap tm;
+  if (int rc = make_map_bf16_2d(&tm, qkv_bf16, (int64_t)h * 3 * Dh, (int64_t)B * S, (int64_t)h * 3 * Dh, 64, 128)) return rc;
+  static bool attr = false;
+  if (!attr) {
+    NPT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::TOTAL));
+    attr = true;
+  }
+  const int grid = B * h * (S / 128);
+  attn_fwd_kernel<<<grid, AT_THREADS, AttnFwdSmem::TOTAL, (cudaStream_t)stream>>>(
+      tm, (__nv_bfloat16*)out_bf16, lse, B, S, h, 1.0f / divisor);
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t npt_attention_bwd_workspace_bytes(int32_t B, int32_t S, int32_t h) { return (size_t)B * S * h * sizeof(float); }
+
+int npt_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse,
+                      void* dqkv_bf16, int32_t B, int32_t S, int32_t h, int32_t Dh, float divisor, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape("attention_bwd", B, S, h, Dh)) return rc;
+  NPT_REQUIRE(workspace && workspace_bytes >= npt_attention_bwd_workspace_bytes(B, S, h), "attention_bwd: workspace too small");
+  NPT_REQUIRE(aligned16(qkv_bf16) && aligned16(out_bf16) && aligned16(d_out_bf16) && aligned16(dqkv_bf16),
+              "attention_bwd: buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* D = (float*)workspace;
+  const int64_t rows = (int64_t)B * S * h;
+  attn_bwd_prep_kernel<<<(unsigned)cdiv(rows * 8, 256), 256, 0, st>>>((const __nv_bfloat16*)out_bf16,
+                                                                      (const __nv_bfloat16*)d_out_bf16, D, rows, S, h);
+  NPT_LAUNCH_CHECK();
+  CUtensorMap tmQKV, tmDO;
+  if (int rc = make_map_bf16_2d(&tmQKV, qkv_bf16, (int64_t)h * 3 * Dh, (int64_t)B * S, (int64_t)h * 3 * Dh, 64, 128)) return rc;
+  if (int rc = make_map_bf16_2d(&tmDO, d_out_bf16, (int64_t)h * Dh, (int64_t)B * S, (int64_t)h * Dh, 64, 128)) return rc;
+  static bool attr = false;
+  if (!attr) {
+    NPT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDkvSmem::TOTAL));
+    NPT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem::TOTAL));
+    attr = true;
+  }
+  const int grid = B * h * (S / 128);
+  const float inv_div = 1.0f / divisor;
+  attn_bwd_dkv_kernel<<<grid, AT_THREADS, AttnDkvSmem::TOTAL, st>>>(tmQKV, tmDO, lse, D, (__nv_bfloat16*)dqkv_bf16, B, S, h, inv_div);
+  NPT_LAUNCH_CHECK();
+  attn_bwd_dq_kernel<<<grid, AT_THREADS, AttnDqSmem::TOTAL, st>>>(tmQKV, tmDO, lse, D, (__nv_bfloat16*)dqkv_bf16, B, S, h, inv_div);
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -58,6 +58,15 @@ class Attention(Model):
         if bf16:
             assert seq_len % 8 == 0 and dh % 8 == 0, "bf16 mode needs seq_len and head_dim to be multiples of 8"
         divisor = float(np.float32(d_model**0.5))                           # attention.py:48
+        if bf16 and ops.attention_supported(seq_len, dh):
+            # fused tcgen05 attention: scores / probabilities never leave the SM
+            att_b, lse = ops.attention_fwd(qkv, batch_size, seq_len, h, dh, divisor)
+            outputs = self.out_projection.forward(att_b)
+            self.ctx |= {"qkv": qkv, "att": att_b, "lse": lse, "divisor": divisor,
+                         "shape": (batch_size, seq_len, h, dh)}
+            if self.is_scattered and npdist.tensor_parallel_size() > 1:
+                npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
+            return outputs
         nb = batch_size * h
         q_op = self._operand(qkv)
         head = (seq_len * ld, dh3)                                          # (batch, head) strides in qkv
@@ -86,6 +95,14 @@ class Attention(Model):
     def backward(self, d_out):
         batch_size, seq_len, h, dh = self.ctx.pop("shape")
         qkv = self.ctx.pop("qkv")
+        if "lse" in self.ctx:  # fused path
+            att_b, lse, divisor = self.ctx.pop("att"), self.ctx.pop("lse"), self.ctx.pop("divisor")
+            d_att = self.out_projection.backward(d_out, out="bf16")
+            d_qkv = ops.attention_bwd(qkv, att_b, d_att, lse, batch_size, seq_len, h, dh, divisor)
+            d_in = self.qkv_projection.backward(d_qkv)
+            if self.is_scattered and npdist.tensor_parallel_size() > 1:
+                npdist.all_reduce(d_in, group=npdist.tensor_parallel_group())
+            return d_in
         p = self.ctx.pop("attention_weights")
         bf16 = rt.is_bf16()
         ld = h * 3 * dh

@@ -184,6 +184,33 @@ def softmax_causal_bwd(p, dp, divisor, want_bf16=False, bf16_only=False):
     return ds
 
 
+# ---- fused attention (bf16 mode) ------------------------------------------------------------------------
+def attention_supported(S: int, Dh: int) -> bool:
+    return bool(_lib.load().npt_attention_supported(S, Dh))
+
+
+def attention_fwd(qkv_b, B, S, h, Dh, divisor):
+    """qkv_b (B,S,h*3*Dh) bf16 -> (out (B,S,h*Dh) bf16, lse (B,h,S) fp32)."""
+    lib = _lib_()
+    assert qkv_b.dtype == _BF16 and qkv_b.is_contiguous()
+    out = rt.empty((B, S, h * Dh), _BF16)
+    lse = rt.empty((B, h, S))
+    check(lib.npt_attention_fwd(_p(qkv_b), _p(out), _p(lse), B, S, h, Dh, divisor, rt.stream()), "npt_attention_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv_b, out_b, d_out_b, lse, B, S, h, Dh, divisor):
+    """-> dqkv (B,S,h*3*Dh) bf16."""
+    lib = _lib_()
+    assert d_out_b.dtype == _BF16 and d_out_b.is_contiguous()
+    dqkv = rt.empty((B, S, h * 3 * Dh), _BF16)
+    need = lib.npt_attention_bwd_workspace_bytes(B, S, h)
+    ws = rt.workspace(need)
+    check(lib.npt_attention_bwd(_p(qkv_b), _p(out_b), _p(d_out_b), _p(lse), _p(dqkv), B, S, h, Dh, divisor,
+                                ws.data_ptr(), ws.numel(), rt.stream()), "npt_attention_bwd")
+    return dqkv
+
+
 # ---- embeddings ----------------------------------------------------------------------------------------
 def embedding_gather(tokens, E, pos, S, chunk_start, chunk_end, masked, want_bf16=False):
     lib = _lib_()

@@ -178,6 +178,42 @@ def test_gemm_batched_head_layout(mode):
     assert not got[:, :, :, 0, :].any() and not got[:, :, :, 2, :].any()
 
 
+@pytest.mark.parametrize("B,S,h", [(1, 128, 1), (2, 256, 3), (1, 512, 2), (3, 256, 6)])
+def test_fused_attention_fwd_bwd(B, S, h):
+    """Flash-style tcgen05 attention against the reference's arithmetic (attention.py:43-52, 81-98)
+    evaluated in fp64 on the same bf16-rounded inputs; scale = 1/sqrt(d_model) with d_model = 384."""
+    Dh, div = 64, float(np.float32(384**0.5))
+    rng = np.random.default_rng(S + h)
+    qkv = bf16_round(rng.standard_normal((B, S, h, 3, Dh)) * 2.0)
+    d_out = bf16_round(rng.standard_normal((B, S, h, Dh)))
+    q, k, v = (qkv[:, :, :, i, :].transpose(0, 2, 1, 3).astype(np.float64) for i in range(3))
+    mask = np.tri(S, S, dtype=bool)
+    s = np.where(mask, q @ k.transpose(0, 1, 3, 2) / div, -np.inf)
+    mx = s.max(-1, keepdims=True)
+    e = np.exp(s - mx)
+    p = e / e.sum(-1, keepdims=True)
+    out_ref = (p @ v).transpose(0, 2, 1, 3)                          # (B,S,h,Dh)
+    lse_ref = (mx + np.log(e.sum(-1, keepdims=True)))[..., 0]          # (B,h,S)
+    qkv_t = dev(qkv.reshape(B, S, -1)).bfloat16()
+    out, lse = ops.attention_fwd(qkv_t, B, S, h, Dh, div)
+    close(host(out).reshape(B, S, h, Dh), out_ref, 1e-2)
+    close(host(lse), lse_ref, 1e-4)
+    # backward (uses the bf16 forward output for D = sum(dO*O), as the kernel does)
+    do = d_out.transpose(0, 2, 1, 3).astype(np.float64)                # (B,h,S,Dh)
+    dv = p.transpose(0, 1, 3, 2) @ do
+    dp = do @ v.transpose(0, 1, 3, 2)
+    ds = np.where(mask, p * (dp - (dp * p).sum(-1, keepdims=True)), 0) / div
+    dq = ds @ k
+    dk = ds.transpose(0, 1, 3, 2) @ q
+    dqkv_ref = np.stack([dq, dk, dv], axis=3).transpose(0, 2, 1, 3, 4)  # (B,S,h,3,Dh)
+    dqkv = ops.attention_bwd(qkv_t, out, dev(d_out.reshape(B, S, -1)).bfloat16(), lse, B, S, h, Dh, div)
+    got = host(dqkv).reshape(B, S, h, 3, Dh)
+    for i, name in enumerate(("dq", "dk", "dv")):
+        ref = dqkv_ref[:, :, :, i]
+        err = np.abs(got[:, :, :, i] - ref).max() / np.abs(ref).max()
+        assert err < 2e-2, (name, err)
+
+
 def test_cast_bf16_padding():
     x = np.random.default_rng(0).standard_normal((37, 65)).astype(np.float32)
     out = host(ops.cast_bf16(dev(x), pad_cols=True))
