@@ -5,11 +5,12 @@
 //   np.add.at(grad.T, tok[~mask], d_out[~mask])
 // bit for bit: for every vocab column the rows of d_out are added ONE BY ONE in increasing
 // flattened (b,s) order onto the value already in grad.  No float atomics:
-//   1) integer histogram of in-chunk tokens          (int atomics: order-independent result)
-//   2) exclusive scan -> segment offsets
-//   3) stable rank of every token inside its segment
-//   4) order[offset+rank] = t
-//   5) one block per vocab column walks its segment in order.
+//   1) per 256-token chunk: integer histogram table[chunk][v] and the stable rank of every token
+//      among the equal tokens of its own chunk (256^2/2 comparisons in shared memory);
+//   2) column scan of the table over chunks (-> tokens of earlier chunks) and scan over v (-> segment
+//      offsets);
+//   3) order[offset[v] + earlier[chunk][v] + rank] = t;
+//   4) one block per (vocab column, 128-wide slice of d) walks its segment in order.
 #include "common.cuh"
 
 namespace npt {
@@ -52,17 +53,41 @@ add_pos_kernel(const float* x, const float* __restrict__ pos, float* out, __nv_b
 }
 
 // ---- scatter-add ------------------------------------------------------------------------------
+constexpr int kSaChunk = 256;
+
 __device__ __forceinline__ int local_id(int tok, int chunk_start, int chunk_end) {
   return (tok < chunk_start || tok >= chunk_end) ? -1 : tok - chunk_start;
 }
 
+// Per chunk of 256 tokens: rank[t] = #{t' < t in the same chunk with the same token};
+// table[chunk][v] = number of in-chunk tokens with local id v (table pre-zeroed).
+__global__ void __launch_bounds__(kSaChunk)
+sa_chunk_kernel(const uint16_t* __restrict__ tokens, int* __restrict__ table, int* __restrict__ rank,
+                int64_t T, int V, int chunk_start, int chunk_end) {
+  __shared__ int ids[kSaChunk];
+  const int64_t t = (int64_t)blockIdx.x * kSaChunk + threadIdx.x;
+  const int v = (t < T) ? local_id(tokens[t], chunk_start, chunk_end) : -1;
+  ids[threadIdx.x] = v;
+  __syncthreads();
+  if (v < 0) return;
+  int r = 0;
+  for (int i = 0; i < (int)threadIdx.x; ++i) r += (ids[i] == v);
+  rank[t] = r;
+  atomicAdd(table + (size_t)blockIdx.x * V + v, 1);  // integer: result independent of order
+}
+
+// Column scan over chunks, in place: table[c][v] <- sum_{c' < c} table[c'][v]; counts[v] <- total.
 __global__ void __launch_bounds__(256)
-sa_count_kernel(const uint16_t* __restrict__ tokens, int* __restrict__ counts, int64_t T,
-                int chunk_start, int chunk_end) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  const int v = local_id(tokens[t], chunk_start, chunk_end);
-  if (v >= 0) atomicAdd(counts + v, 1);
+sa_colscan_kernel(int* __restrict__ table, int* __restrict__ counts, int nchunks, int V) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  int run = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const int n = table[(size_t)c * V + v];
+    table[(size_t)c * V + v] = run;
+    run += n;
+  }
+  counts[v] = run;
 }
 
 // Single block exclusive scan of counts[0..V) into offsets[0..V].
@@ -77,14 +102,13 @@ sa_scan_kernel(const int* __restrict__ counts, int* __restrict__ offsets, int V)
   for (int i = lo; i < hi; ++i) s += counts[i];
   part[threadIdx.x] = s;
   __syncthreads();
-  // Hillis-Steele inclusive scan over 1024 partials
-  for (int o = 1; o < 1024; o <<= 1) {
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan over the 1024 partials
     int add = (threadIdx.x >= o) ? part[threadIdx.x - o] : 0;
     __syncthreads();
     part[threadIdx.x] += add;
     __syncthreads();
   }
-  int run = part[threadIdx.x] - s;  // exclusive prefix of this thread's chunk
+  int run = part[threadIdx.x] - s;
   for (int i = lo; i < hi; ++i) {
     offsets[i] = run;
     run += counts[i];
@@ -92,58 +116,56 @@ sa_scan_kernel(const int* __restrict__ counts, int* __restrict__ offsets, int V)
   if (threadIdx.x == 1023) offsets[V] = part[1023];
 }
 
-// rank[t] = #{t' < t : tok[t'] == tok[t]}; then order[offsets[v] + rank] = t.
-constexpr int kRankTile = 2048;
 __global__ void __launch_bounds__(256)
-sa_rank_fill_kernel(const uint16_t* __restrict__ tokens, const int* __restrict__ offsets,
-                    int* __restrict__ order, int64_t T, int chunk_start, int chunk_end) {
-  __shared__ uint16_t tile[kRankTile];
+sa_fill_kernel(const uint16_t* __restrict__ tokens, const int* __restrict__ table, const int* __restrict__ rank,
+               const int* __restrict__ offsets, int* __restrict__ order, int64_t T, int V, int chunk_start,
+               int chunk_end) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t t_block_end = min((int64_t)(blockIdx.x + 1) * blockDim.x, T);  // exclusive
-  const int mytok = (t < T) ? tokens[t] : -1;
-  int rank = 0;
-  for (int64_t base = 0; base < t_block_end; base += kRankTile) {
-    const int64_t lim = min((int64_t)kRankTile, t_block_end - base);
-    __syncthreads();
-    for (int i = threadIdx.x; i < lim; i += blockDim.x) tile[i] = tokens[base + i];
-    __syncthreads();
-    if (t < T) {
-      const int64_t upto = min(lim, t - base);  // only t' < t
-      for (int64_t i = 0; i < upto; ++i) rank += (tile[i] == mytok);
-    }
-  }
-  if (t < T) {
-    const int v = local_id(mytok, chunk_start, chunk_end);
-    if (v >= 0) order[offsets[v] + rank] = (int)t;
-  }
+  if (t >= T) return;
+  const int v = local_id(tokens[t], chunk_start, chunk_end);
+  if (v < 0) return;
+  const int64_t c = t / kSaChunk;
+  order[offsets[v] + table[(size_t)c * V + v] + rank[t]] = (int)t;
 }
 
-// One block per vocab column; threads over d.  Sequential fp32 adds in segment order.
+// grid (V, ceil(d/128)); sequential fp32 adds in segment order, 8 loads in flight per thread.
 __global__ void __launch_bounds__(128)
 sa_accumulate_kernel(const int* __restrict__ offsets, const int* __restrict__ order,
                      const float* __restrict__ d_out, float* __restrict__ grad, int64_t ldG, int d) {
   const int v = blockIdx.x;
   const int beg = offsets[v], end = offsets[v + 1];
-  if (beg == end) return;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float acc = grad[(int64_t)c * ldG + v];
-    int i = beg;
-    for (; i + 4 <= end; i += 4) {  // loads are independent of the adds: issue 4 at a time
-      const float a0 = d_out[(int64_t)order[i] * d + c];
-      const float a1 = d_out[(int64_t)order[i + 1] * d + c];
-      const float a2 = d_out[(int64_t)order[i + 2] * d + c];
-      const float a3 = d_out[(int64_t)order[i + 3] * d + c];
-      acc = __fadd_rn(acc, a0);
-      acc = __fadd_rn(acc, a1);
-      acc = __fadd_rn(acc, a2);
-      acc = __fadd_rn(acc, a3);
-    }
-    for (; i < end; ++i) acc = __fadd_rn(acc, d_out[(int64_t)order[i] * d + c]);
-    grad[(int64_t)c * ldG + v] = acc;
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  if (beg == end || c >= d) return;
+  float acc = grad[(int64_t)c * ldG + v];
+  int i = beg;
+  for (; i + 8 <= end; i += 8) {
+    int idx[8];
+    float a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) idx[u] = __ldg(order + i + u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = __ldg(d_out + (int64_t)idx[u] * d + c);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, a[u]);  // strictly in order
   }
+  for (; i < end; ++i) acc = __fadd_rn(acc, __ldg(d_out + (int64_t)__ldg(order + i) * d + c));
+  grad[(int64_t)c * ldG + v] = acc;
 }
 
 static size_t sa_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct SaLayout {
+  size_t table, counts, offsets, rank, order, total;
+  SaLayout(int64_t T, int V) {
+    const size_t nchunks = (size_t)cdiv(T, kSaChunk);
+    table = 0;
+    counts = table + sa_align(nchunks * V * 4);
+    offsets = counts + sa_align((size_t)(V + 1) * 4);
+    rank = offsets + sa_align((size_t)(V + 1) * 4);
+    order = rank + sa_align((size_t)T * 4);
+    total = order + sa_align((size_t)T * 4);
+  }
+};
 
 }  // namespace npt
 
@@ -174,7 +196,7 @@ int npt_add_pos(const float* x, const float* pos, float* out, void* x_bf16, int6
 }
 
 size_t npt_embedding_scatter_add_workspace_bytes(int64_t T, int32_t V_local) {
-  return sa_align((size_t)(V_local + 1) * 4) * 2 + sa_align((size_t)T * 4);
+  return SaLayout(T, V_local).total;
 }
 
 int npt_embedding_scatter_add(const uint16_t* tokens, const float* d_out, float* grad, int64_t ldG,
@@ -184,22 +206,28 @@ int npt_embedding_scatter_add(const uint16_t* tokens, const float* d_out, float*
   NPT_REQUIRE(T > 0 && d > 0 && V_local > 0, "scatter_add: bad shape");
   NPT_REQUIRE(chunk_end - chunk_start <= V_local, "scatter_add: chunk wider than V_local");
   NPT_REQUIRE(T < (int64_t)1 << 31, "scatter_add: T too large");
-  NPT_REQUIRE(workspace && workspace_bytes >= npt_embedding_scatter_add_workspace_bytes(T, V_local),
-              "scatter_add: workspace too small");
+  const SaLayout L(T, V_local);
+  NPT_REQUIRE(workspace && workspace_bytes >= L.total, "scatter_add: workspace too small (%zu < %zu)", workspace_bytes, L.total);
   (void)masked;
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
-  int* counts = (int*)ws;
-  int* offsets = (int*)(ws + sa_align((size_t)(V_local + 1) * 4));
-  int* order = (int*)(ws + 2 * sa_align((size_t)(V_local + 1) * 4));
-  NPT_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(V_local + 1) * 4, st));
-  sa_count_kernel<<<(unsigned)cdiv(T, 256), 256, 0, st>>>(tokens, counts, T, chunk_start, chunk_end);
+  int* table = (int*)(ws + L.table);
+  int* counts = (int*)(ws + L.counts);
+  int* offsets = (int*)(ws + L.offsets);
+  int* rank = (int*)(ws + L.rank);
+  int* order = (int*)(ws + L.order);
+  const int nchunks = (int)cdiv(T, kSaChunk);
+  NPT_CHECK_CUDA(cudaMemsetAsync(table, 0, (size_t)nchunks * V_local * 4, st));
+  sa_chunk_kernel<<<nchunks, kSaChunk, 0, st>>>(tokens, table, rank, T, V_local, chunk_start, chunk_end);
+  NPT_LAUNCH_CHECK();
+  sa_colscan_kernel<<<(unsigned)cdiv(V_local, 256), 256, 0, st>>>(table, counts, nchunks, V_local);
   NPT_LAUNCH_CHECK();
   sa_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, V_local);
   NPT_LAUNCH_CHECK();
-  sa_rank_fill_kernel<<<(unsigned)cdiv(T, 256), 256, 0, st>>>(tokens, offsets, order, T, chunk_start, chunk_end);
+  sa_fill_kernel<<<(unsigned)cdiv(T, 256), 256, 0, st>>>(tokens, table, rank, offsets, order, T, V_local, chunk_start, chunk_end);
   NPT_LAUNCH_CHECK();
-  sa_accumulate_kernel<<<(unsigned)V_local, 128, 0, st>>>(offsets, order, d_out, grad, ldG, d);
+  dim3 grid((unsigned)V_local, (unsigned)cdiv(d, 128));
+  sa_accumulate_kernel<<<grid, 128, 0, st>>>(offsets, order, d_out, grad, ldG, d);
   NPT_LAUNCH_CHECK();
   return 0;
 }

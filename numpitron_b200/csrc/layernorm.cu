@@ -131,42 +131,67 @@ ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
     ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float inv_d = 1.0f / (float)d;
-  for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < rows;
-       row += (int64_t)gridDim.x * kLnWarps) {
-    const float mean = mean_in[row], var = var_in[row];
-    const float denom = sqrtf(var + eps);
-    const float stdv = sqrtf(var);  // inputs.std(): no eps (normalization.py:48-50)
-    const float4* xr = reinterpret_cast<const float4*>(x + row * d);
-    const float4* dr = reinterpret_cast<const float4*>(dy + row * d);
-    float4 xh[NV], w[NV];
-    float s1 = 0.f, s2 = 0.f;
+  // Two rows per warp iteration: all loads of both rows are issued before either row's
+  // reductions, which doubles the bytes in flight per warp (the kernel is latency-bound otherwise).
+  const int64_t stride = (int64_t)gridDim.x * kLnWarps;
+  for (int64_t row0 = (int64_t)blockIdx.x * kLnWarps + warp; row0 < rows; row0 += 2 * stride) {
+    float4 xv[2][NV], dv[2][NV];
+    float mean[2], denom[2], stdv[2];
+    bool live[2];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + i * 32;
-      if (c < nvec) {
-        const float4 xv = ld_stream(xr + c), dv = ld_stream(dr + c);
-        xh[i].x = __fdiv_rn(xv.x - mean, denom); xh[i].y = __fdiv_rn(xv.y - mean, denom);
-        xh[i].z = __fdiv_rn(xv.z - mean, denom); xh[i].w = __fdiv_rn(xv.w - mean, denom);
-        w[i].x = g[i].x * dv.x; w[i].y = g[i].y * dv.y; w[i].z = g[i].z * dv.z; w[i].w = g[i].w * dv.w;
-        s1 += (xh[i].x * w[i].x + xh[i].y * w[i].y) + (xh[i].z * w[i].z + xh[i].w * w[i].w);
-        s2 += (w[i].x + w[i].y) + (w[i].z + w[i].w);
-        ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
-        ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+    for (int u = 0; u < 2; ++u) {
+      const int64_t row = row0 + u * stride;
+      live[u] = row < rows;
+      if (live[u]) {
+        const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+        const float4* dr = reinterpret_cast<const float4*>(dy + row * d);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = lane + i * 32;
+          if (c < nvec) { xv[u][i] = ld_stream(xr + c); dv[u][i] = ld_stream(dr + c); }
+        }
+        mean[u] = mean_in[row];
+        const float var = var_in[row];
+        denom[u] = sqrtf(var + eps);
+        stdv[u] = sqrtf(var);  // inputs.std(): no eps (normalization.py:48-50)
       }
     }
-    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
-    float4* outr = reinterpret_cast<float4*>(dx + row * d);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + i * 32;
-      if (c < nvec) {
-        float4 o;
-        o.x = __fdiv_rn(w[i].x - c1 * xh[i].x - c2, stdv);
-        o.y = __fdiv_rn(w[i].y - c1 * xh[i].y - c2, stdv);
-        o.z = __fdiv_rn(w[i].z - c1 * xh[i].z - c2, stdv);
-        o.w = __fdiv_rn(w[i].w - c1 * xh[i].w - c2, stdv);
-        if (dx) st_stream(outr + c, o);
-        if (dxb) st_bf16x4(dxb + row * d + (int64_t)c * 4, o);
+    for (int u = 0; u < 2; ++u) {
+      if (!live[u]) continue;  // warp-uniform
+      const int64_t row = row0 + u * stride;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + i * 32;
+        if (c < nvec) {
+          float4& xh = xv[u][i];  // becomes x-hat in place
+          const float4 g4v = g[i], dd = dv[u][i];
+          xh.x = __fdiv_rn(xh.x - mean[u], denom[u]); xh.y = __fdiv_rn(xh.y - mean[u], denom[u]);
+          xh.z = __fdiv_rn(xh.z - mean[u], denom[u]); xh.w = __fdiv_rn(xh.w - mean[u], denom[u]);
+          ag[i].x += dd.x * xh.x; ag[i].y += dd.y * xh.y; ag[i].z += dd.z * xh.z; ag[i].w += dd.w * xh.w;
+          ab[i].x += dd.x; ab[i].y += dd.y; ab[i].z += dd.z; ab[i].w += dd.w;
+          float4& w = dv[u][i];   // becomes gamma*dy in place
+          w.x = g4v.x * dd.x; w.y = g4v.y * dd.y; w.z = g4v.z * dd.z; w.w = g4v.w * dd.w;
+          s1 += (xh.x * w.x + xh.y * w.y) + (xh.z * w.z + xh.w * w.w);
+          s2 += (w.x + w.y) + (w.z + w.w);
+        }
+      }
+      const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+      float4* outr = reinterpret_cast<float4*>(dx + row * d);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + i * 32;
+        if (c < nvec) {
+          const float4 xh = xv[u][i], w = dv[u][i];
+          float4 o;
+          o.x = __fdiv_rn(w.x - c1 * xh.x - c2, stdv[u]);
+          o.y = __fdiv_rn(w.y - c1 * xh.y - c2, stdv[u]);
+          o.z = __fdiv_rn(w.z - c1 * xh.z - c2, stdv[u]);
+          o.w = __fdiv_rn(w.w - c1 * xh.w - c2, stdv[u]);
+          if (dx) st_stream(outr + c, o);
+          if (dxb) st_bf16x4(dxb + row * d + (int64_t)c * 4, o);
+        }
       }
     }
   }
@@ -228,17 +253,29 @@ ln_bwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma
 }
 
 // Stage 2: out[c] = sum_b partial[b][c]   (fixed order -> deterministic)
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out0,
-                                       float* __restrict__ out1, int nblocks, int d) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * d) return;
+// 32 columns x 32 row-lanes per block: every lane sums a strided subset of the partial rows
+// (independent loads in flight), then a fixed-order smem tree adds the 32 lanes.
+__global__ void __launch_bounds__(1024)
+reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out0,
+                       float* __restrict__ out1, int nblocks, int d) {
+  __shared__ float sm[32][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float t = 0.f;
-  for (int b = 0; b < nblocks; ++b) t += partial[(size_t)b * 2 * d + c];
-  if (c < d) out0[c] = t; else out1[c - d] = t;
+  if (c < 2 * d)
+    for (int b = ry; b < nblocks; b += 32) t += partial[(size_t)b * 2 * d + c];
+  sm[ry][cx] = t;
+  __syncthreads();
+  if (ry == 0 && c < 2 * d) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) s += sm[k][cx];
+    if (c < d) out0[c] = s; else out1[c - d] = s;
+  }
 }
 
 static int ln_bwd_blocks(int64_t rows) {
-  int64_t want = cdiv(rows, kLnWarps);
+  int64_t want = cdiv(rows, 2 * kLnWarps);
   int64_t cap = (int64_t)sm_count() * 2;
   return (int)(want < cap ? want : cap);
 }
@@ -340,9 +377,7 @@ int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, con
                                                   (__nv_bfloat16*)dx_bf16, partial, rows, d, eps);
     NPT_LAUNCH_CHECK();
   }
-  const int threads = 256;
-  reduce_partials_kernel<<<(unsigned)cdiv(2 * (int64_t)d, threads), threads, 0, st>>>(
-      partial, dgamma, dbeta, nblocks, d);
+  reduce_partials_kernel<<<(unsigned)cdiv(2 * (int64_t)d, 32), 1024, 0, st>>>(partial, dgamma, dbeta, nblocks, d);
   NPT_LAUNCH_CHECK();
   return 0;
 }
