@@ -38,7 +38,8 @@ __device__ __forceinline__ void store_row_chunk(uint8_t* tile, int row, int c, c
     u.y = pack2(v[8 * q + 2], v[8 * q + 3]);
     u.z = pack2(v[8 * q + 4], v[8 * q + 5]);
     u.w = pack2(v[8 * q + 6], v[8 * q + 7]);
-    *reinterpret_cast<uint4*>(base + swz128(row, (c & 1) * 4 + q)) = u;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(base) + swz128(row, (c & 1) * 4 + q)), "r"(u.x),
+                 "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
   }
 }
 

@@ -156,13 +156,23 @@ colsum_stage1_vec_kernel(const void* __restrict__ xv, int64_t ld, float* __restr
   }
 }
 
-__global__ void colsum_stage2_kernel(const float* __restrict__ partial, float* __restrict__ out,
-                                     int nparts, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// Stage 2: 32 columns x 32 row-lanes per block (independent loads), fixed-order smem tree.
+__global__ void __launch_bounds__(1024)
+colsum_stage2_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int cols) {
+  __shared__ float sm[32][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float t = 0.f;
-  for (int b = 0; b < nparts; ++b) t += partial[(size_t)b * cols + c];
-  out[c] = t;
+  if (c < cols)
+    for (int b = ry; b < nparts; b += 32) t += partial[(size_t)b * cols + c];
+  sm[ry][cx] = t;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) s += sm[k][cx];
+    out[c] = s;
+  }
 }
 
 static int colsum_parts(int64_t rows, int cols) {
@@ -243,7 +253,7 @@ int npt_colsum(const void* x, int32_t x_is_bf16, int64_t ld, float* out, int64_t
     colsum_stage1_kernel<<<grid, 256, 0, st>>>(x, x_is_bf16, ld, (float*)workspace, rows, cols, rpb);
   }
   NPT_LAUNCH_CHECK();
-  colsum_stage2_kernel<<<(unsigned)cdiv(cols, 256), 256, 0, st>>>((const float*)workspace, out, parts, cols);
+  colsum_stage2_kernel<<<(unsigned)cdiv(cols, 32), 1024, 0, st>>>((const float*)workspace, out, parts, cols);
   NPT_LAUNCH_CHECK();
   return 0;
 }

@@ -107,6 +107,23 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Explicit shared-space accesses (the staging pointers come from an integer round-up, so the
+// compiler would otherwise emit slower generic LD/ST for them).
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts64u(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): SWIZZLE_128B, version 1.
 //   K-major : LBO unused (1), SBO = 1024 B between 8-row groups.
 //   MN-major: LBO = bytes between 64-element MN chunks, SBO = 1024 B between 8-k groups.
@@ -366,8 +383,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= epi.alpha;
           if (epi.bias) {
+            if (epi.bias_vec4 && nb + 32 <= p.N) {  // eight 16-byte broadcast loads instead of 32 scalar ones
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += (nb + j < p.N) ? __ldg(epi.bias + nb + j) : 0.f;
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(epi.bias + nb) + j);
+                v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += (nb + j < p.N) ? __ldg(epi.bias + nb + j) : 0.f;
+            }
           }
           if (epi.relu) {
 #pragma unroll
@@ -378,14 +403,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ++store_i;
         uint8_t* s32 = stage_base + bufsel * L::EPI_F32;
         uint8_t* s16 = stage_base + 2 * L::EPI_F32 + bufsel * L::EPI_BF16;
+        const uint32_t s32a = smem_u32(s32), s16a = smem_u32(s16);
         // the TMA store that last read this buffer (two chunks ago) must have finished reading it
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
         if (want_f32 || masked) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)  // SWIZZLE_128B: 16-byte chunk j of row r lands at chunk j ^ (r & 7)
-            *reinterpret_cast<float4*>(s32 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            sts128(s32a + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         if (masked) {
           if (mask_fast) {
@@ -402,17 +427,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = i * 4 + (lane >> 3), ch = lane & 7;
-            float4* sp = reinterpret_cast<float4*>(s32 + row * 128 + ((ch ^ (row & 7)) << 4));
-            float4 x = *sp;
+            const uint32_t sp = s32a + row * 128 + ((ch ^ (row & 7)) << 4);
+            float4 x = lds128(sp);
             const uint32_t mb = mbits >> (4 * i);
             x.x = (mb & 1u) ? x.x : 0.f; x.y = (mb & 2u) ? x.y : 0.f;
             x.z = (mb & 4u) ? x.z : 0.f; x.w = (mb & 8u) ? x.w : 0.f;
-            if (want_f32) *sp = x;
+            if (want_f32) sts128(sp, x.x, x.y, x.z, x.w);
             if (want_bf16) {  // SWIZZLE_64B: 16-byte chunk q of row r lands at chunk q ^ ((r >> 1) & 3)
               uint2 u;
               u.x = pack_bf16(x.x, x.y);
               u.y = pack_bf16(x.z, x.w);
-              *reinterpret_cast<uint2*>(s16 + row * 64 + (((ch >> 1) ^ ((row >> 1) & 3)) << 4) + ((ch & 1) << 3)) = u;
+              sts64u(s16a + row * 64 + (((ch >> 1) ^ ((row >> 1) & 3)) << 4) + ((ch & 1) << 3), u.x, u.y);
             }
           }
         } else if (want_bf16) {
@@ -423,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
             u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]);
             u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
-            *reinterpret_cast<uint4*>(s16 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = u;
+            sts128u(s16a + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), u.x, u.y, u.z, u.w);
           }
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
