@@ -35,6 +35,7 @@ class GemmArgs(C.Structure):
         ("mask_is_bf16", c_int32),
         ("ldmask", c_int64), ("stride_mask_outer", c_int64), ("stride_mask_inner", c_int64),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("relu_bits_out", c_void_p), ("mask_bits", c_void_p), ("ld_bits", c_int64),
     ]
 
 

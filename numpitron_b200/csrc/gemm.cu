@@ -24,6 +24,7 @@ GemmEpilogue make_epilogue(const npt_gemm_args& a) {
     e.mask_vec4 = 0;
   }
   e.bias_vec4 = a.bias && aligned16(a.bias);
+  e.bits_out = a.relu_bits_out; e.bits_in = a.mask_bits; e.ld_bits = a.ld_bits;
   return e;
 }
 
@@ -90,6 +91,11 @@ int npt_gemm(const npt_gemm_args* args, void* stream) {
   NPT_REQUIRE(!a.C || a.ldc >= a.N, "gemm: ldc too small");
   NPT_REQUIRE(!a.C_bf16 || a.ldcb >= a.N, "gemm: ldcb too small");
   NPT_REQUIRE(!a.mask || a.ldmask >= a.N, "gemm: ldmask too small");
+  if (a.relu_bits_out || a.mask_bits) {
+    NPT_REQUIRE(a.mode == NPT_GEMM_BF16_TC && a.batch == 1, "gemm: packed ReLU bits need the bf16 tensor-core mode and batch == 1");
+    NPT_REQUIRE(a.ld_bits * 32 >= a.N, "gemm: ld_bits too small");
+    NPT_REQUIRE(!a.relu_bits_out || a.relu, "gemm: relu_bits_out needs relu = 1");
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (a.mode != NPT_GEMM_FP32_SIMT) {
     if (int rc = gemm_tc_supported(a)) return rc;

@@ -13,6 +13,7 @@ struct GemmEpilogue {
   const void* mask; int mask_bf16; int64_t ldm, smo, smi;
   int M, N, batch_inner;
   int c_vec4, cb_vec4, mask_vec4, bias_vec4;  // host-checked alignment of 4-wide accesses
+  uint32_t* bits_out; const uint32_t* bits_in; int64_t ld_bits;  // packed ReLU mask (tensor-core path)
 };
 
 __device__ __forceinline__ float epi_value(const GemmEpilogue& e, int64_t mask_off, int n, float acc) {

@@ -316,6 +316,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
       if (masked && p.tma_store) prefetch_mask(0);
+      // packed ReLU mask: one 32-bit word per (row, 32-column chunk); the whole tile's words for this
+      // lane's row are fetched here, before the wait on the accumulator.
+      uint32_t mwords[BN / 32];
+      if (epi.bits_in) {
+#pragma unroll
+        for (int cc = 0; cc < BN / 32; ++cc)
+          mwords[cc] = (m < p.M && n0 + cc * 32 < p.N) ? __ldg(epi.bits_in + (int64_t)m * epi.ld_bits + (n0 >> 5) + cc) : 0u;
+      }
       mbar_wait(tmem_full_bar + acc, (tile_i >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -397,6 +405,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (epi.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (epi.bits_in) {  // packed ReLU mask: this lane's row, this chunk's 32 columns = one word
+            const uint32_t w = mwords[c];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ((w >> j) & 1u) ? v[j] : 0.f;
+          }
+          if (epi.bits_out && m < p.M) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+            epi.bits_out[(int64_t)m * epi.ld_bits + (nb >> 5)] = w;
           }
         }
         const uint32_t bufsel = store_i & 1;
@@ -541,6 +560,7 @@ static int tc_bn(const npt_gemm_args& a) {
 }
 
 int gemm_tc_splits(const npt_gemm_args& a) {
+  if (a.relu_bits_out || a.mask_bits) return 1;  // the packed-mask epilogue runs in the GEMM kernel itself
   const int bn = tc_bn(a);
   const int64_t tiles = cdiv(a.M, TC_BM) * cdiv(a.N, bn) * a.batch;
   const int64_t kblocks = cdiv(a.K, TC_BK);
@@ -595,6 +615,7 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
   NPT_REQUIRE(total < ((int64_t)1 << 31), "gemm(tc): too many tiles");
   p.total_tiles = (int)total;
   p.raw = splits > 1;
+  NPT_REQUIRE(!(p.raw && (a.relu_bits_out || a.mask_bits)), "gemm(tc): packed ReLU bits are not supported with split-K");
   // Can the outputs be written by TMA?  (16-byte aligned base, pitches and batch strides)
   if (p.raw) {
     p.tma_store = (a.N % 4 == 0) && aligned16(partial);
@@ -608,6 +629,8 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
     const bool cb_ok = !a.C_bf16 || (aligned16(a.C_bf16) && a.ldcb % 8 == 0 && a.stride_cb_outer % 8 == 0 &&
                                      a.stride_cb_inner % 8 == 0);
     p.tma_store = c_ok && cb_ok;
+    NPT_REQUIRE(p.tma_store || !(a.relu_bits_out || a.mask_bits),
+                "gemm(tc): packed ReLU bits need TMA-storable outputs (16-byte aligned base and pitches)");
     if (p.tma_store && a.C) {
       rc = make_map(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B, a.C, a.N, a.M, a.ldc, n_bi,
                     a.stride_c_inner, n_bo, a.stride_c_outer, 32, 32);

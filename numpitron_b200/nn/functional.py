@@ -55,15 +55,22 @@ def _result(y, yb):
     return y
 
 
-def linear_forward(x, layer, wname="weight", bias=None, relu=False, out="f32"):
-    """y = x @ W (+ b) (ReLU) — nn/linear.py:44-47.  x (..., d_in), W (d_in, d_out)."""
+def relu_bits_supported(d_out: int) -> bool:
+    """Packed ReLU-mask words are produced by the tensor-core epilogue (bf16 mode, TMA-storable N)."""
+    return rt.is_bf16() and d_out % 8 == 0
+
+
+def linear_forward(x, layer, wname="weight", bias=None, relu=False, out="f32", relu_bits=None):
+    """y = x @ W (+ b) (ReLU) — nn/linear.py:44-47.  x (..., d_in), W (d_in, d_out).
+    `relu_bits`: optional int32 (T, ceil(d_out/32)) buffer that receives the packed (y > 0) mask."""
     W = getattr(layer, wname).data
     d_in, d_out = W.shape
     T = x.numel() // d_in
     A, lda = _act(x)
     B, ldb = _weight(layer, wname)
     y, yb = _outputs((*x.shape[:-1], d_out), out)
-    ops.gemm(A, B, T, d_out, d_in, lda=lda, ldb=ldb, C_out=y, ldc=d_out, Cb_out=yb, ldcb=d_out, bias=bias, relu=relu)
+    ops.gemm(A, B, T, d_out, d_in, lda=lda, ldb=ldb, C_out=y, ldc=d_out, Cb_out=yb, ldcb=d_out, bias=bias, relu=relu,
+             relu_bits_out=relu_bits)
     return _result(y, yb)
 
 
@@ -86,11 +93,14 @@ def linear_backward_input(dy, layer, wname="weight", mask=None, out="f32"):
     A, lda = _act(dy)
     B, ldb = _weight(layer, wname)
     dx, dxb = _outputs((*dy.shape[:-1], d_in), out)
-    mk, ldm = (None, 0)
+    mk, ldm, bits = None, 0, None
     if mask is not None:
-        mk, ldm = mask, mask.shape[-1]
+        if mask.dtype == torch.int32:
+            bits = mask  # packed (hidden > 0) words written by the forward GEMM
+        else:
+            mk, ldm = mask, mask.shape[-1]
     ops.gemm(A, B, T, d_in, d_out, lda=lda, ldb=ldb, trans_b=True, C_out=dx, ldc=d_in, Cb_out=dxb, ldcb=d_in,
-             mask=mk, ldmask=ldm)
+             mask=mk, ldmask=ldm, mask_bits=bits)
     return _result(dx, dxb)
 
 

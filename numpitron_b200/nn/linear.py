@@ -21,10 +21,10 @@ class Linear(Layer):
 
     # `relu`, `mask` and `out` are the hooks MLP / Attention use to fuse ReLU into this layer's GEMM
     # epilogues and to keep GEMM-to-GEMM tensors in bf16 only (bf16 mode).
-    def forward(self, inputs, relu: bool = False, out: str = "f32"):
+    def forward(self, inputs, relu: bool = False, out: str = "f32", relu_bits=None):
         """outputs = inputs @ W (+ b) — one GEMM with the bias (and ReLU) in its epilogue."""
         bias = self.bias.data if self.use_bias else None
-        outputs = F.linear_forward(inputs, self, "weight", bias=bias, relu=relu, out=out)
+        outputs = F.linear_forward(inputs, self, "weight", bias=bias, relu=relu, out=out, relu_bits=relu_bits)
         self.ctx["inputs"] = inputs
         return outputs
 

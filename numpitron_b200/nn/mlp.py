@@ -2,7 +2,11 @@
 Drop-in for the reference's nn/mlp.py; the ReLU lives in the GEMM epilogues."""
 from __future__ import annotations
 
+import torch
+
 from .. import distributed as npdist
+from .. import runtime as rt
+from . import functional as F
 from .activation import ReLU
 from .linear import Linear
 from .model import Model
@@ -21,15 +25,21 @@ class MLP(Model):
     def forward(self, inputs):
         # max(0, x@W1+b1) in one GEMM epilogue; the post-ReLU tensor doubles as the backward mask
         # because relu(a) > 0  <=>  a > 0.  It only feeds GEMMs, so bf16 mode keeps it in bf16 alone.
-        hidden = self.column_linear.forward(inputs, relu=True, out="bf16")
+        d_hidden = self.column_linear.weight.data.shape[1]
+        bits = None
+        if F.relu_bits_supported(d_hidden):
+            # 1 bit per element (hidden > 0), packed by the forward epilogue: the backward reads these
+            # 3 MB instead of the 50 MB bf16 activation
+            bits = rt.empty((inputs.numel() // inputs.shape[-1], (d_hidden + 31) // 32), torch.int32)
+        hidden = self.column_linear.forward(inputs, relu=True, out="bf16", relu_bits=bits)
+        self.ctx["relu_mask"] = bits if bits is not None else hidden
         outputs = self.row_linear.forward(hidden)
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
             npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
         return outputs
 
     def backward(self, d_out):
-        hidden = self.row_linear.ctx["inputs"]
-        d_out = self.row_linear.backward(d_out, mask=hidden, out="bf16")  # (dy@W2^T) * (a>0)
+        d_out = self.row_linear.backward(d_out, mask=self.ctx.pop("relu_mask"), out="bf16")  # (dy@W2^T) * (a>0)
         d_out = self.column_linear.backward(d_out)
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
             npdist.all_reduce(d_out, group=npdist.tensor_parallel_group())

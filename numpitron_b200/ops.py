@@ -28,7 +28,8 @@ def _p(t, off=0):
 def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_off=0,
          a_strides=(0, 0), b_strides=(0, 0), C_out=None, ldc=0, c_off=0, c_strides=(0, 0),
          Cb_out=None, ldcb=0, cb_off=0, cb_strides=(0, 0), batch=1, batch_inner=1, alpha=1.0,
-         bias=None, relu=False, mask=None, ldmask=0, mask_off=0, mask_strides=(0, 0), mode=None):
+         bias=None, relu=False, mask=None, ldmask=0, mask_off=0, mask_strides=(0, 0), mode=None,
+         relu_bits_out=None, mask_bits=None):
     """C[b] = alpha * op(A[b]) op(B[b]) (+bias)(ReLU)(*mask>0) — see npt_gemm in the header.
 
     strides are (outer, inner) in elements.  A/B must be fp32 for mode 0 and bf16 for mode 1.
@@ -56,6 +57,10 @@ def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_of
     if mask is not None:
         g.mask, g.mask_is_bf16 = _p(mask, mask_off), int(mask.dtype == _BF16)
         g.ldmask, g.stride_mask_outer, g.stride_mask_inner = ldmask, mask_strides[0], mask_strides[1]
+    if relu_bits_out is not None or mask_bits is not None:
+        bits = relu_bits_out if relu_bits_out is not None else mask_bits
+        assert bits.dtype == torch.int32 and bits.shape[-1] * 32 >= N
+        g.relu_bits_out, g.mask_bits, g.ld_bits = _p(relu_bits_out), _p(mask_bits), bits.shape[-1]
     need = lib.npt_gemm_workspace_bytes(C.byref(g))
     if need:
         ws = rt.workspace(need)

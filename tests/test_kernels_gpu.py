@@ -142,6 +142,38 @@ def test_gemm_bf16_persistent_many_tiles_and_fused_epilogues():
     np.testing.assert_array_equal(host(dxb2), host(dxb))
 
 
+@pytest.mark.parametrize("M,K,N", [(16384, 384, 1536), (300, 136, 200), (128, 64, 72)])
+def test_gemm_packed_relu_bits(M, K, N):
+    """The forward epilogue packs (relu output > 0) into 1 bit/element; the backward GEMM consuming those
+    words must equal the one consuming the bf16 activation as mask (ReLU.backward, activation.py:42-43)."""
+    rng = np.random.default_rng(M + N)
+    x = dev(bf16_round(rng.standard_normal((M, K)))).bfloat16()
+    w = dev(bf16_round(rng.standard_normal((K, N)) * 0.1)).bfloat16()
+    bias = dev(rng.standard_normal(N).astype(np.float32))
+    nw = (N + 31) // 32
+    bits = torch.full((M, nw), -1, dtype=torch.int32, device="cuda")
+    hb = rt.empty((M, N), torch.bfloat16)
+    h = rt.empty((M, N))
+    ops.gemm(x, w, M, N, K, lda=K, ldb=N, C_out=h, ldc=N, Cb_out=hb, ldcb=N, bias=bias, relu=True, relu_bits_out=bits, mode=1)
+    got = host(bits).view(np.uint32)
+    want = np.zeros((M, nw), np.uint32)
+    pos = host(h) > 0
+    for j in range(N):
+        want[:, j // 32] |= pos[:, j].astype(np.uint32) << np.uint32(j % 32)
+    valid = np.full(nw, 0xFFFFFFFF, np.uint32)
+    if N % 32:
+        valid[-1] = (1 << (N % 32)) - 1
+    np.testing.assert_array_equal(got & valid, want)
+    dy = dev(bf16_round(rng.standard_normal((M, K)))).bfloat16()
+    w2 = dev(bf16_round(rng.standard_normal((N, K)) * 0.1)).bfloat16()
+    a, b = rt.empty((M, N)), rt.empty((M, N))
+    ab, bb = rt.empty((M, N), torch.bfloat16), rt.empty((M, N), torch.bfloat16)
+    ops.gemm(dy, w2, M, N, K, lda=K, ldb=K, trans_b=True, C_out=a, ldc=N, Cb_out=ab, ldcb=N, mask=hb, ldmask=N, mode=1)
+    ops.gemm(dy, w2, M, N, K, lda=K, ldb=K, trans_b=True, C_out=b, ldc=N, Cb_out=bb, ldcb=N, mask_bits=bits, mode=1)
+    np.testing.assert_array_equal(host(a), host(b))
+    np.testing.assert_array_equal(host(ab), host(bb))
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_gemm_batched_head_layout(mode):
     """q@k^T and p@v addressed in place inside the (B,S,h,3,Dh) projection output (attention.py:43-52)."""
