@@ -63,6 +63,8 @@ class GraphedTrainStep:
         self.warmup = warmup
         self._eager_steps = 0
         self.stream = torch.cuda.Stream()
+        # parameters / shadows were produced on the caller's stream: order the step stream after it
+        self.stream.wait_stream(torch.cuda.current_stream())
 
     # -- bodies -----------------------------------------------------------------------------------
     def _compute(self):
