@@ -187,4 +187,4 @@ def init(tp_size: int = 1, pp_size: int = 1, dp_size: int = 1) -> None:
     st.model_parallel_group = add_group([ranks[:, dp_rank, :].reshape(-1) for dp_rank in range(dp_size)])
 
 
-from .collectives import all_gather, all_reduce, broadcast, scatter  # noqa: E402,F401
+from .collectives import all_gather, all_reduce, all_reduce_async, broadcast, scatter  # noqa: E402,F401

@@ -49,6 +49,25 @@ def all_reduce(tensor, op: str = "sum", group=None) -> None:
     return None
 
 
+class _Done:
+    def wait(self):
+        return None
+
+
+def all_reduce_async(tensor: torch.Tensor, op: str = "sum", group=None):
+    """Start an in-place all-reduce of a device buffer and return a handle with `.wait()`.
+
+    Extension used inside the layers (not part of the reference API): the backward TP all-reduce of
+    dX (call sites C4/C5) is started as soon as dX exists and overlaps the dW / db kernels, which do
+    not depend on it.  `.wait()` orders the current stream after the collective (no host sync)."""
+    group = group or _default_group()
+    if group.Get_size() == 1:
+        return _Done()
+    work = dist.all_reduce(tensor, op=_OPS[op], group=group.pg, async_op=True)
+    rt.drop_bf16(tensor)
+    return work
+
+
 def broadcast(tensor, src: int = 0, group=None) -> None:
     group = group or _default_group()
     if group.Get_size() == 1:

@@ -99,10 +99,7 @@ class Attention(Model):
             att_b, lse, divisor = self.ctx.pop("att"), self.ctx.pop("lse"), self.ctx.pop("divisor")
             d_att = self.out_projection.backward(d_out, out="bf16")
             d_qkv = ops.attention_bwd(qkv, att_b, d_att, lse, batch_size, seq_len, h, dh, divisor)
-            d_in = self.qkv_projection.backward(d_qkv)
-            if self.is_scattered and npdist.tensor_parallel_size() > 1:
-                npdist.all_reduce(d_in, group=npdist.tensor_parallel_group())
-            return d_in
+            return self._qkv_backward(d_qkv)
         p = self.ctx.pop("attention_weights")
         bf16 = rt.is_bf16()
         ld = h * 3 * dh
@@ -135,7 +132,15 @@ class Attention(Model):
                  batch=nb, batch_inner=h, **into_qkv(0))
         ops.gemm(ds_op, qkv_op, seq_len, dh, seq_len, lda=seq_len, ldb=ld, trans_a=True, b_off=0, a_strides=mat,
                  b_strides=head, batch=nb, batch_inner=h, **into_qkv(dh))
-        d_in = self.qkv_projection.backward(d_qkv_b if bf16 else d_qkv)
+        return self._qkv_backward(d_qkv_b if bf16 else d_qkv)
+
+    def _qkv_backward(self, d_qkv):
+        """QKV-projection backward; under TP the all-reduce of dX (attention.py:101-102) is started as
+        soon as dX is enqueued and overlaps the dW GEMM."""
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
-            npdist.all_reduce(d_in, group=npdist.tensor_parallel_group())
-        return d_in
+            pending = []
+            d_in = self.qkv_projection.backward(
+                d_qkv, on_dx=lambda dx: pending.append(npdist.all_reduce_async(dx, group=npdist.tensor_parallel_group())))
+            pending[0].wait()
+            return d_in
+        return self.qkv_projection.backward(d_qkv)

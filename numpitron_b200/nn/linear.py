@@ -28,10 +28,15 @@ class Linear(Layer):
         self.ctx["inputs"] = inputs
         return outputs
 
-    def backward(self, d_out, mask=None, out: str = "f32"):
-        """dW = x^T dy (replaces, never accumulates), db = sum dy, returns dx = dy W^T."""
+    def backward(self, d_out, mask=None, out: str = "f32", on_dx=None):
+        """dW = x^T dy (replaces, never accumulates), db = sum dy, returns dx = dy W^T.
+        `on_dx(dx)` (optional) is called as soon as dx is enqueued — the tensor-parallel callers
+        start their all-reduce there so it overlaps the dW / db kernels."""
         inputs = self.ctx.pop("inputs")
+        d_in = F.linear_backward_input(d_out, self, "weight", mask=mask, out=out)
+        if on_dx is not None:
+            on_dx(d_in)
         self.update_parameter("weight", gradient=F.linear_backward_weight(inputs, d_out))
         if self.use_bias:
             self.update_parameter("bias", gradient=F.bias_grad(d_out))
-        return F.linear_backward_input(d_out, self, "weight", mask=mask, out=out)
+        return d_in

@@ -40,7 +40,11 @@ class MLP(Model):
 
     def backward(self, d_out):
         d_out = self.row_linear.backward(d_out, mask=self.ctx.pop("relu_mask"), out="bf16")  # (dy@W2^T) * (a>0)
-        d_out = self.column_linear.backward(d_out)
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
-            npdist.all_reduce(d_out, group=npdist.tensor_parallel_group())
-        return d_out
+            # all-reduce of dX (mlp.py:52-53) overlapped with the column-linear dW / db kernels
+            pending = []
+            d_out = self.column_linear.backward(
+                d_out, on_dx=lambda dx: pending.append(npdist.all_reduce_async(dx, group=npdist.tensor_parallel_group())))
+            pending[0].wait()
+            return d_out
+        return self.column_linear.backward(d_out)
