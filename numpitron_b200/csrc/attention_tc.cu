@@ -7,15 +7,18 @@
 // the merged (B,S,h*Dh) head output.  The score scale is the caller's `divisor` (= sqrt(d_model),
 // NOT sqrt(head_dim): Q3).
 //
-// All three kernels share one shape: warp 0 = TMA producer, warp 1 = tcgen05 MMA issuer, warps 2-5
-// = one thread per query row (TMEM lane) doing the softmax arithmetic.  128x128 score tiles live in
-// TMEM; P / dS go through 128B-swizzled shared memory as the A operand of the second GEMM — read
-// K-major (P@V, dS@K) or MN-major (P^T@dO, dS^T@Q) from the same bytes; Q / dO / K / V tiles are
-// likewise read K-major or MN-major from the same TMA box.
-//   fwd : CTA = (b, head, 128 queries); loops over key tiles 0..diag (online softmax, fp32 running
+// All three kernels are PERSISTENT (one CTA per SM walks a static list of work items) and share one
+// shape: warp 0 = TMA producer, warp 1 = tcgen05 MMA issuer, warps 2-5 = one thread per query (or
+// key) row = TMEM lane doing the softmax arithmetic.  128x128 score tiles live in TMEM; P / dS go
+// through 128B-swizzled shared memory as the A operand of the second GEMM — read K-major (P@V, dS@K)
+// or MN-major (P^T@dO, dS^T@Q) from the same bytes; Q / dO / K / V tiles are likewise read K-major
+// or MN-major from the same TMA box.  Loads run two tiles ahead and the MMA warp issues the next
+// score tile before the current tile's second GEMM, so TMA, tensor core and the softmax threads
+// overlap across tiles and across work items.
+//   fwd : item = (b, head, 128 queries); steps = key tiles 0..diag (online softmax, fp32 running
 //         max / sum, O accumulated in registers); writes O (bf16) and the row log-sum-exp.
-//   dkv : CTA = (b, head, 128 keys); loops over query tiles diag..last; dK, dV accumulate in TMEM.
-//   dq  : CTA = (b, head, 128 queries); loops over key tiles 0..diag; dQ accumulates in TMEM.
+//   dkv : item = (b, head, 128 keys); steps = query tiles diag..last; dK, dV accumulate in TMEM.
+//   dq  : item = (b, head, 128 queries); steps = key tiles 0..diag; dQ accumulates in TMEM.
 // No atomics: every output element has exactly one writer and a fixed summation order.
 #include "tc_ptx.cuh"
 
@@ -24,109 +27,160 @@ using namespace tc;
 
 constexpr int AT_THREADS = 192;
 constexpr int AT_TILE = 128 * 64 * 2;  // one {64 x 128} bf16 TMA box = 16 KB
+constexpr int AT_DH = 64;
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) { return pack_bf16(a, b); }
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // Write 32 consecutive bf16 values (cols c*32 .. c*32+31 of a 128-wide row) of `row` into a
-// [2 halves][128 rows][128 B] swizzled tile (half = 64 columns).
-__device__ __forceinline__ void store_row_chunk(uint8_t* tile, int row, int c, const float (&v)[32]) {
-  uint8_t* base = tile + (c >> 1) * 16384;
+// [2 halves][128 rows][128 B] swizzled tile (half = 64 columns); `tile` is a shared-space address.
+__device__ __forceinline__ void store_row_chunk(uint32_t tile, int row, int c, const float (&v)[32]) {
+  const uint32_t base = tile + (c >> 1) * 16384;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack2(v[8 * q], v[8 * q + 1]);
-    u.y = pack2(v[8 * q + 2], v[8 * q + 3]);
-    u.z = pack2(v[8 * q + 4], v[8 * q + 5]);
-    u.w = pack2(v[8 * q + 6], v[8 * q + 7]);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(base) + swz128(row, (c & 1) * 4 + q)), "r"(u.x),
-                 "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + swz128(row, (c & 1) * 4 + q)),
+                 "r"(pack2(v[8 * q], v[8 * q + 1])), "r"(pack2(v[8 * q + 2], v[8 * q + 3])),
+                 "r"(pack2(v[8 * q + 4], v[8 * q + 5])), "r"(pack2(v[8 * q + 6], v[8 * q + 7])) : "memory");
   }
 }
+
+// Walks the (item, step) sequence of one persistent CTA.  Items are (bh, tile) pairs, tile fastest.
+struct Cursor {
+  int w, total, stride, nqt;
+  int bh, tile;       // current item
+  int j, n_steps;     // step inside the item
+  uint32_t t, wi;     // global step / item counters (barrier phases)
+  bool desc;          // tile order inside a bh: descending (heavy query tiles first) or ascending
+  bool key_items;     // steps of an item: (nqt - tile) query tiles [dkv] or (tile + 1) key tiles [fwd, dq]
+  __device__ void load() {
+    // Heaviest tiles of ALL (b, head) pairs first, then the next lighter ones (longest-processing-
+    // time order): a static stride-gridDim walk then gives every CTA the same mix of heavy and light
+    // items instead of pinning the 2-step items on the even CTAs.
+    const int n_bh = total / nqt;
+    const int r = w / n_bh;
+    bh = w - r * n_bh;
+    tile = desc ? nqt - 1 - r : r;
+    n_steps = key_items ? nqt - tile : tile + 1;
+    j = 0;
+  }
+  __device__ void init(int first, int total_, int stride_, int nqt_, bool desc_, bool key_items_) {
+    w = first; total = total_; stride = stride_; nqt = nqt_; desc = desc_; key_items = key_items_;
+    t = 0; wi = 0;
+    if (valid()) load();
+  }
+  __device__ bool valid() const { return w < total; }
+  __device__ bool first_step() const { return j == 0; }
+  __device__ bool last_step() const { return j == n_steps - 1; }
+  __device__ void next() {
+    ++t;
+    if (++j == n_steps) {
+      w += stride;
+      ++wi;
+      if (valid()) load();
+    }
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
 struct AttnFwdSmem {
-  static constexpr int Q = 0, K = AT_TILE, V = 3 * AT_TILE, P = 5 * AT_TILE, BAR = 7 * AT_TILE;
-  static constexpr int TOTAL = BAR + 16 * 8 + 16 + 1024;
+  static constexpr int Q = 0, K = 2 * AT_TILE, V = 4 * AT_TILE, P = 6 * AT_TILE, BAR = 10 * AT_TILE;
+  static constexpr int TOTAL = BAR + 24 * 8 + 16 + 1024;
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out,
                 float* __restrict__ lse, int B, int S, int h, float inv_div) {
-  constexpr int DH = 64;
+  constexpr int DH = AT_DH;
+  using L = AttnFwdSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdSmem::BAR);
-  uint64_t *q_full = bars, *k_full = bars + 1, *v_full = bars + 3, *kv_empty = bars + 5, *s_full = bars + 7,
-           *s_empty = bars + 8, *p_full = bars + 9, *pv_done = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+  uint64_t *q_full = bars, *q_empty = bars + 2, *k_full = bars + 4, *v_full = bars + 6, *kv_empty = bars + 8,
+           *s_full = bars + 10, *s_empty = bars + 12, *p_full = bars + 14, *pv_done = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqt = S / 128;
-  const int qt = nqt - 1 - (int)(blockIdx.x % nqt);  // heavy (late) query tiles first
-  const int bh = blockIdx.x / nqt;
-  const int b = bh / h, hh = bh - b * h;
-  const int n_kv = qt + 1;
-  const int col_q = hh * 3 * DH, col_k = col_q + DH, col_v = col_q + 2 * DH;
-  const int row0 = b * S;
+  const int total = B * h * nqt;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(kv_empty + s, 1); }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);
-    mbar_init(p_full, 4);
-    mbar_init(pv_done, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full + s, 1); mbar_init(q_empty + s, 1);
+      mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(kv_empty + s, 1);
+      mbar_init(s_full + s, 1); mbar_init(s_empty + s, 4);
+      mbar_init(p_full + s, 4); mbar_init(pv_done + s, 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
+  // TMEM columns: S[2] at 0 / 128, O[2] at 256 / 320
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, AT_TILE);
-      tma_load_4d(&tmQKV, q_full, smem + AttnFwdSmem::Q, col_q, row0 + qt * 128, 0, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(kv_empty + st, ((j >> 1) & 1) ^ 1);
+      Cursor c;
+      for (c.init(blockIdx.x, total, gridDim.x, nqt, true, false); c.valid(); c.next()) {
+        const int b = c.bh / h, hh = c.bh - b * h;
+        const int col_q = hh * 3 * DH, row0 = b * S;
+        if (c.first_step()) {
+          const int qb = c.wi & 1;
+          mbar_wait(q_empty + qb, ((c.wi >> 1) & 1) ^ 1);
+          mbar_expect_tx(q_full + qb, AT_TILE);
+          tma_load_4d(&tmQKV, q_full + qb, smem + L::Q + qb * AT_TILE, col_q, row0 + c.tile * 128, 0, 0);
+        }
+        const int st = c.t & 1;
+        mbar_wait(kv_empty + st, ((c.t >> 1) & 1) ^ 1);
         mbar_expect_tx(k_full + st, AT_TILE);
-        tma_load_4d(&tmQKV, k_full + st, smem + AttnFwdSmem::K + st * AT_TILE, col_k, row0 + j * 128, 0, 0);
+        tma_load_4d(&tmQKV, k_full + st, smem + L::K + st * AT_TILE, col_q + DH, row0 + c.j * 128, 0, 0);
         mbar_expect_tx(v_full + st, AT_TILE);
-        tma_load_4d(&tmQKV, v_full + st, smem + AttnFwdSmem::V + st * AT_TILE, col_v, row0 + j * 128, 0, 0);
+        tma_load_4d(&tmQKV, v_full + st, smem + L::V + st * AT_TILE, col_q + 2 * DH, row0 + c.j * 128, 0, 0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(128, false, false);  // S = Q K^T : both K-major
       constexpr uint32_t idesc_o = make_idesc(DH, false, true);    // O = P V   : P K-major, V MN-major
-      const uint32_t sq = smem_u32(smem + AttnFwdSmem::Q), sp = smem_u32(smem + AttnFwdSmem::P);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1, ph = (j >> 1) & 1;
-        const uint32_t sk = smem_u32(smem + AttnFwdSmem::K + st * AT_TILE), sv = smem_u32(smem + AttnFwdSmem::V + st * AT_TILE);
+      auto issue_qk = [&](const Cursor& c) {
+        const int st = c.t & 1, ph = (c.t >> 1) & 1, qb = c.wi & 1;
+        if (c.first_step()) mbar_wait(q_full + qb, (c.wi >> 1) & 1);
         mbar_wait(k_full + st, ph);
-        if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+        mbar_wait(s_empty + st, ph ^ 1);  // softmax threads have drained this S buffer (two steps ago)
         fence_after();
-        const uint64_t dq = make_smem_desc(sq, 16, 1024), dk = make_smem_desc(sk, 16, 1024);
+        const uint64_t dq = make_smem_desc(smem_u32(smem + L::Q + qb * AT_TILE), 16, 1024);
+        const uint64_t dk = make_smem_desc(smem_u32(smem + L::K + st * AT_TILE), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0);
-        umma_commit(s_full);
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem + st * 128, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0);
+        umma_commit(s_full + st);
+        if (c.last_step()) umma_commit(q_empty + qb);
+      };
+      Cursor cq, cp;
+      cq.init(blockIdx.x, total, gridDim.x, nqt, true, false);
+      cp = cq;
+      if (cq.valid()) { issue_qk(cq); cq.next(); }
+      for (; cp.valid(); cp.next()) {
+        if (cq.valid()) { issue_qk(cq); cq.next(); }  // next score tile runs while this tile's softmax is in flight
+        const int st = cp.t & 1, ph = (cp.t >> 1) & 1;
         mbar_wait(v_full + st, ph);
-        mbar_wait(p_full, j & 1);
+        mbar_wait(p_full + st, ph);
         fence_after();
-        const uint64_t dv = make_smem_desc(sv, 16384, 1024);
+        const uint32_t sp = smem_u32(smem + L::P + st * 2 * AT_TILE);
+        const uint64_t dv = make_smem_desc(smem_u32(smem + L::V + st * AT_TILE), 16384, 1024);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // 128 keys = 8 x 16
           const uint64_t dp = make_smem_desc(sp + (k >> 2) * 16384, 16, 1024) + (uint64_t)((k & 3) * 2);
-          umma_bf16(tmem_O, dp, dv + (uint64_t)(k * 128), idesc_o, k > 0);
+          umma_bf16(tmem + 256 + st * 64, dp, dv + (uint64_t)(k * 128), idesc_o, k > 0);
         }
-        umma_commit(pv_done);
+        umma_commit(pv_done + st);
         umma_commit(kv_empty + st);
       }
     }
@@ -134,78 +188,105 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    uint8_t* sP = smem + AttnFwdSmem::P;
     float m_run = -INFINITY, l_run = 0.f;
     float o[DH];
+    const float k2 = inv_div * 1.4426950408889634f;  // log2(e) / sqrt(d_model)
+    Cursor c;
+    for (c.init(blockIdx.x, total, gridDim.x, nqt, true, false); c.valid(); c.next()) {
+      const int st = c.t & 1, ph = (c.t >> 1) & 1;
+      const bool diag = c.last_step();  // the last key tile of a query tile is its diagonal tile
+      if (c.first_step()) {
+        m_run = -INFINITY; l_run = 0.f;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) o[d] = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      const bool diag = (j == qt);
-      mbar_wait(s_full, j & 1);
-      fence_after();
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_S + lane_addr + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int t = 0; t < 32; ++t)
-          if (!diag || c * 32 + t <= row) mx = fmaxf(mx, __uint_as_float(r[t]) * inv_div);
+        for (int d = 0; d < DH; ++d) o[d] = 0.f;
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = (j == 0) ? 0.f : __expf(m_run - m_new);
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_S + lane_addr + c * 32, r);
-        tmem_ld_wait();
-        float p[32];
+      const uint32_t tS = tmem + st * 128 + lane_addr, tO = tmem + 256 + st * 64 + lane_addr;
+      const uint32_t sP = smem_u32(smem + L::P + st * 2 * AT_TILE);
+      mbar_wait(s_full + st, ph);
+      fence_after();
+      // The whole 128-wide score row goes to registers in one shot, so the TMEM buffer is handed back
+      // to the MMA warp before any arithmetic.  Softmax runs in the log2 domain: x2 = s * (log2e / div),
+      // p = 2^(x2 - m2): one FFMA + one MUFU.EX2 per element; masking only on the diagonal tile.
+      uint32_t r[4][32];
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const bool ok = !diag || c * 32 + t <= row;
-          p[t] = ok ? __expf(__uint_as_float(r[t]) * inv_div - m_new) : 0.f;
-          sum += p[t];
+      for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32(tS + cc * 32, r[cc]);
+      tmem_ld_wait();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty + st);
+      float mx = -INFINITY;
+      if (diag) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            if (cc * 32 + t <= row) mx = fmaxf(mx, __uint_as_float(r[cc][t]));
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+          for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(r[cc][t]));
+      }
+      const float m_new = fmaxf(m_run, mx * k2);  // k2 > 0, so max commutes with the scaling
+      const float alpha = c.first_step() ? 0.f : ex2f(m_run - m_new);
+      float sum = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float p[32];
+        if (diag) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            p[t] = (cc * 32 + t <= row) ? ex2f(fmaf(__uint_as_float(r[cc][t]), k2, -m_new)) : 0.f;
+            sum += p[t];
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            p[t] = ex2f(fmaf(__uint_as_float(r[cc][t]), k2, -m_new));
+            sum += p[t];
+          }
         }
-        store_row_chunk(sP, row, c, p);
+        store_row_chunk(sP, row, cc, p);
       }
       l_run = l_run * alpha + sum;
       m_run = m_new;
-      fence_before();          // TMEM reads of S are complete
+      fence_before();          // TMEM reads of O two steps ago are complete
       fence_proxy_async();     // P writes visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
-      mbar_wait(pv_done, j & 1);
+      if (lane == 0) mbar_arrive(p_full + st);
+      mbar_wait(pv_done + st, ph);
       fence_after();
 #pragma unroll
-      for (int c = 0; c < DH / 32; ++c) {
+      for (int cc = 0; cc < DH / 32; ++cc) {
         uint32_t r[32];
-        tmem_ld_32x32(tmem_O + lane_addr + c * 32, r);
+        tmem_ld_32x32(tO + cc * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 32; ++t) o[c * 32 + t] = o[c * 32 + t] * alpha + __uint_as_float(r[t]);
+        for (int t = 0; t < 32; ++t) o[cc * 32 + t] = o[cc * 32 + t] * alpha + __uint_as_float(r[t]);
+      }
+      if (c.last_step()) {
+        const int b = c.bh / h, hh = c.bh - b * h;
+        const float inv_l = 1.0f / l_run;
+        const int64_t q_glob = (int64_t)b * S + c.tile * 128 + row;
+        __nv_bfloat16* orow = out + (q_glob * h + hh) * DH;
+#pragma unroll
+        for (int q = 0; q < DH / 8; ++q) {
+          uint4 u;
+          u.x = pack2(o[8 * q] * inv_l, o[8 * q + 1] * inv_l);
+          u.y = pack2(o[8 * q + 2] * inv_l, o[8 * q + 3] * inv_l);
+          u.z = pack2(o[8 * q + 4] * inv_l, o[8 * q + 5] * inv_l);
+          u.w = pack2(o[8 * q + 6] * inv_l, o[8 * q + 7] * inv_l);
+          *reinterpret_cast<uint4*>(orow + 8 * q) = u;
+        }
+        lse[((int64_t)b * h + hh) * S + c.tile * 128 + row] = m_run * 0.6931471805599453f + __logf(l_run);  // natural log
       }
     }
-    const float inv_l = 1.0f / l_run;
-    const int64_t q_glob = (int64_t)row0 + qt * 128 + row;
-    __nv_bfloat16* orow = out + (q_glob * h + hh) * DH;
-#pragma unroll
-    for (int q = 0; q < DH / 8; ++q) {
-      uint4 u;
-      u.x = pack2(o[8 * q] * inv_l, o[8 * q + 1] * inv_l);
-      u.y = pack2(o[8 * q + 2] * inv_l, o[8 * q + 3] * inv_l);
-      u.z = pack2(o[8 * q + 4] * inv_l, o[8 * q + 5] * inv_l);
-      u.w = pack2(o[8 * q + 6] * inv_l, o[8 * q + 7] * inv_l);
-      *reinterpret_cast<uint4*>(orow + 8 * q) = u;
-    }
-    lse[((int64_t)b * h + hh) * S + qt * 128 + row] = m_run + __logf(l_run);
   }
   fence_before();
   __syncthreads();
   if (warp == 1) {
     fence_after();
-    tmem_dealloc<256>(tmem);
+    tmem_dealloc<512>(tmem);
   }
 }
 
@@ -243,23 +324,35 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* _
 
 // ------------------------------------------------------------------------------------------------
 // backward, shared row arithmetic: p = exp(s/div - lse), dS = p*(dP - D)/div, both to smem tiles.
+// `wait_tiles` is polled (once) right before the first shared-memory store.
 // ------------------------------------------------------------------------------------------------
 template <bool WRITE_P>
-__device__ __forceinline__ void bwd_rows(uint32_t tmem_S, uint32_t tmem_dP, uint32_t lane_addr, int row, bool diag,
-                                         float lse_r, float D_r, float inv_div, uint8_t* sP, uint8_t* sdS) {
+__device__ __forceinline__ void bwd_rows(uint32_t tS, uint32_t tdP, int row, bool diag, float lse_r, float D_r,
+                                         float inv_div, uint32_t sP, uint32_t sdS, uint64_t* wait_tiles,
+                                         uint32_t wait_parity) {
+  const float k2 = inv_div * 1.4426950408889634f, lse2 = lse_r * 1.4426950408889634f;  // log2 domain
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     uint32_t rs[32], rp[32];
-    tmem_ld_32x32(tmem_S + lane_addr + c * 32, rs);
-    tmem_ld_32x32(tmem_dP + lane_addr + c * 32, rp);
+    tmem_ld_32x32(tS + c * 32, rs);
+    tmem_ld_32x32(tdP + c * 32, rp);
     tmem_ld_wait();
     float p[32], ds[32];
+    if (diag) {
 #pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      const bool ok = !diag || c * 32 + t <= row;   // key index <= query index
-      p[t] = ok ? __expf(__uint_as_float(rs[t]) * inv_div - lse_r) : 0.f;
-      ds[t] = p[t] * (__uint_as_float(rp[t]) - D_r) * inv_div;
+      for (int t = 0; t < 32; ++t) {
+        const bool ok = c * 32 + t <= row;   // key index <= query index
+        p[t] = ok ? ex2f(fmaf(__uint_as_float(rs[t]), k2, -lse2)) : 0.f;
+        ds[t] = p[t] * (__uint_as_float(rp[t]) - D_r) * inv_div;
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        p[t] = ex2f(fmaf(__uint_as_float(rs[t]), k2, -lse2));
+        ds[t] = p[t] * (__uint_as_float(rp[t]) - D_r) * inv_div;
+      }
     }
+    if (c == 0 && wait_tiles) mbar_wait(wait_tiles, wait_parity);  // previous P / dS tiles consumed by the MMAs
     if (WRITE_P) store_row_chunk(sP, row, c, p);
     store_row_chunk(sdS, row, c, ds);
   }
@@ -284,46 +377,43 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, __nv_bfloat16* dst
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward dK / dV : CTA = (b, head, key tile j); loops over query tiles i = j .. nqt-1
+// backward dK / dV : item = (b, head, key tile j); steps = query tiles i = j .. nqt-1
 // ------------------------------------------------------------------------------------------------
 struct AttnDkvSmem {
-  static constexpr int K = 0, V = AT_TILE, Q = 2 * AT_TILE, DO = 4 * AT_TILE, P = 6 * AT_TILE, DS = 8 * AT_TILE,
-                       BAR = 10 * AT_TILE;
-  static constexpr int TOTAL = BAR + 16 * 8 + 16 + 1024;
+  static constexpr int K = 0, V = 2 * AT_TILE, Q = 4 * AT_TILE, DO = 6 * AT_TILE, P = 8 * AT_TILE, DS = 10 * AT_TILE,
+                       BAR = 12 * AT_TILE;
+  static constexpr int TOTAL = BAR + 24 * 8 + 16 + 1024;
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const float* __restrict__ lse, const float* __restrict__ D, __nv_bfloat16* __restrict__ dqkv,
                     int B, int S, int h, float inv_div) {
-  constexpr int DH = 64;
+  constexpr int DH = AT_DH;
   using L = AttnDkvSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
-  uint64_t *kv_full = bars, *qdo_full = bars + 1, *qdo_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 6,
-           *pds_full = bars + 7, *acc_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t *kv_full = bars, *kv_empty = bars + 2, *qdo_full = bars + 4, *qdo_empty = bars + 6, *s_full = bars + 8,
+           *s_empty = bars + 9, *pds_full = bars + 10, *acc_done = bars + 11, *out_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqt = S / 128;
-  const int j = (int)(blockIdx.x % nqt);  // key tile; tile 0 has the most work and comes first
-  const int bh = blockIdx.x / nqt;
-  const int b = bh / h, hh = bh - b * h;
-  const int n_it = nqt - j;               // query tiles j .. nqt-1
-  const int col_q = hh * 3 * DH, col_k = col_q + DH, col_v = col_q + 2 * DH;
-  const int col_do = hh * DH;
-  const int row0 = b * S;
+  const int total = B * h * nqt;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
-    mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full + s, 1); mbar_init(qdo_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1);
+      mbar_init(qdo_full + s, 1); mbar_init(qdo_empty + s, 1);
+    }
     mbar_init(s_full, 1);
     mbar_init(s_empty, 4);
     mbar_init(pds_full, 4);
     mbar_init(acc_done, 1);
+    mbar_init(out_done, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -335,75 +425,103 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(kv_full, 2 * AT_TILE);
-      tma_load_4d(&tmQKV, kv_full, smem + L::K, col_k, row0 + j * 128, 0, 0);
-      tma_load_4d(&tmQKV, kv_full, smem + L::V, col_v, row0 + j * 128, 0, 0);
-      for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1, i = j + it;
-        mbar_wait(qdo_empty + st, ((it >> 1) & 1) ^ 1);
+      Cursor c;
+      for (c.init(blockIdx.x, total, gridDim.x, nqt, false, true); c.valid(); c.next()) {
+        const int b = c.bh / h, hh = c.bh - b * h;
+        const int col_q = hh * 3 * DH, row0 = b * S;
+        if (c.first_step()) {
+          const int kb = c.wi & 1;
+          mbar_wait(kv_empty + kb, ((c.wi >> 1) & 1) ^ 1);
+          mbar_expect_tx(kv_full + kb, 2 * AT_TILE);
+          tma_load_4d(&tmQKV, kv_full + kb, smem + L::K + kb * AT_TILE, col_q + DH, row0 + c.tile * 128, 0, 0);
+          tma_load_4d(&tmQKV, kv_full + kb, smem + L::V + kb * AT_TILE, col_q + 2 * DH, row0 + c.tile * 128, 0, 0);
+        }
+        const int st = c.t & 1, i = c.tile + c.j;
+        mbar_wait(qdo_empty + st, ((c.t >> 1) & 1) ^ 1);
         mbar_expect_tx(qdo_full + st, 2 * AT_TILE);
         tma_load_4d(&tmQKV, qdo_full + st, smem + L::Q + st * AT_TILE, col_q, row0 + i * 128, 0, 0);
-        tma_load_4d(&tmDO, qdo_full + st, smem + L::DO + st * AT_TILE, col_do, row0 + i * 128, 0, 0);
+        tma_load_4d(&tmDO, qdo_full + st, smem + L::DO + st * AT_TILE, hh * DH, row0 + i * 128, 0, 0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(128, false, false);  // S = Q K^T, dP = dO V^T
       constexpr uint32_t idesc_a = make_idesc(DH, true, true);     // dV = P^T dO, dK = dS^T Q : both MN-major
-      const uint32_t sk = smem_u32(smem + L::K), sv = smem_u32(smem + L::V);
       const uint32_t sp = smem_u32(smem + L::P), sds = smem_u32(smem + L::DS);
-      mbar_wait(kv_full, 0);
-      for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1, ph = (it >> 1) & 1;
-        const uint32_t sq = smem_u32(smem + L::Q + st * AT_TILE), sdo = smem_u32(smem + L::DO + st * AT_TILE);
-        mbar_wait(qdo_full + st, ph);
-        if (it > 0) mbar_wait(s_empty, (it - 1) & 1);
+      auto issue_sdp = [&](const Cursor& c) {
+        const int st = c.t & 1, kb = c.wi & 1;
+        if (c.first_step()) mbar_wait(kv_full + kb, (c.wi >> 1) & 1);
+        mbar_wait(qdo_full + st, (c.t >> 1) & 1);
+        mbar_wait(s_empty, (c.t & 1) ^ 1);  // threads have read S / dP of the previous step
         fence_after();
-        const uint64_t dq = make_smem_desc(sq, 16, 1024), dk = make_smem_desc(sk, 16, 1024);
-        const uint64_t ddo = make_smem_desc(sdo, 16, 1024), dv = make_smem_desc(sv, 16, 1024);
+        const uint64_t dq = make_smem_desc(smem_u32(smem + L::Q + st * AT_TILE), 16, 1024);
+        const uint64_t dk = make_smem_desc(smem_u32(smem + L::K + kb * AT_TILE), 16, 1024);
+        const uint64_t ddo = make_smem_desc(smem_u32(smem + L::DO + st * AT_TILE), 16, 1024);
+        const uint64_t dv = make_smem_desc(smem_u32(smem + L::V + kb * AT_TILE), 16, 1024);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_dP, ddo + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), idesc_s, k > 0);
         umma_commit(s_full);
-        mbar_wait(pds_full, it & 1);
+      };
+      Cursor cs, ca;
+      cs.init(blockIdx.x, total, gridDim.x, nqt, false, true);
+      ca = cs;
+      if (cs.valid()) { issue_sdp(cs); cs.next(); }
+      for (; ca.valid(); ca.next()) {
+        const int st = ca.t & 1, kb = ca.wi & 1;
+        mbar_wait(pds_full, ca.t & 1);               // P / dS of this step are in shared memory (S / dP drained)
+        if (cs.valid()) { issue_sdp(cs); cs.next(); }  // next score tiles first: the threads are waiting for them
+        if (ca.first_step()) mbar_wait(out_done, (ca.wi & 1) ^ 1);  // previous item's dK / dV were read out
         fence_after();
         // A = P^T / dS^T : MN-major (M = keys: two 64-key halves 16 KB apart; K = queries: 16 rows = 2048 B)
         // B = dO / Q tile : MN-major (N = Dh, K = queries: 16 rows = 2048 B)
         const uint64_t dpt = make_smem_desc(sp, 16384, 1024), ddst = make_smem_desc(sds, 16384, 1024);
-        const uint64_t dob = make_smem_desc(sdo, 16384, 1024), dqb = make_smem_desc(sq, 16384, 1024);
+        const uint64_t dob = make_smem_desc(smem_u32(smem + L::DO + st * AT_TILE), 16384, 1024);
+        const uint64_t dqb = make_smem_desc(smem_u32(smem + L::Q + st * AT_TILE), 16384, 1024);
+        const bool acc0 = !ca.first_step();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dV, dpt + (uint64_t)(k * 128), dob + (uint64_t)(k * 128), idesc_a, (it > 0 || k > 0));
+        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dV, dpt + (uint64_t)(k * 128), dob + (uint64_t)(k * 128), idesc_a, (acc0 || k > 0));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dK, ddst + (uint64_t)(k * 128), dqb + (uint64_t)(k * 128), idesc_a, (it > 0 || k > 0));
+        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dK, ddst + (uint64_t)(k * 128), dqb + (uint64_t)(k * 128), idesc_a, (acc0 || k > 0));
         umma_commit(acc_done);
         umma_commit(qdo_empty + st);
+        if (ca.last_step()) umma_commit(kv_empty + kb);
       }
     }
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    for (int it = 0; it < n_it; ++it) {
-      const int i = j + it;
+    const uint32_t sP = smem_u32(smem + L::P), sdS = smem_u32(smem + L::DS);
+    Cursor c;
+    for (c.init(blockIdx.x, total, gridDim.x, nqt, false, true); c.valid(); c.next()) {
+      const int b = c.bh / h, hh = c.bh - b * h;
+      const int i = c.tile + c.j;
       const int64_t stat = ((int64_t)b * h + hh) * S + i * 128 + row;
       const float lse_r = lse[stat], D_r = D[stat];
-      mbar_wait(s_full, it & 1);
+      mbar_wait(s_full, c.t & 1);
       fence_after();
-      if (it > 0) mbar_wait(acc_done, (it - 1) & 1);  // P / dS tiles of the previous query tile are consumed
-      bwd_rows<true>(tmem_S, tmem_dP, lane_addr, row, it == 0, lse_r, D_r, inv_div, smem + L::P, smem + L::DS);
+      // P / dS tiles are free once the previous step's dV / dK MMAs retired
+      bwd_rows<true>(tmem_S + lane_addr, tmem_dP + lane_addr, row, c.first_step(), lse_r, D_r, inv_div, sP, sdS,
+                     c.t > 0 ? acc_done : nullptr, (c.t - 1) & 1);
       fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(pds_full); }
+      if (c.last_step()) {
+        mbar_wait(acc_done, c.t & 1);
+        fence_after();
+        // rows of dK / dV are KEYS of tile j
+        const int64_t k_glob = (int64_t)b * S + c.tile * 128 + row;
+        __nv_bfloat16* base = dqkv + (k_glob * h + hh) * 3 * DH;
+        store_acc_row(tmem_dK + lane_addr, base + DH);
+        store_acc_row(tmem_dV + lane_addr, base + 2 * DH);
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(out_done);
+      }
     }
-    mbar_wait(acc_done, (n_it - 1) & 1);
-    fence_after();
-    // rows of dK / dV are KEYS of tile j
-    const int64_t k_glob = (int64_t)row0 + j * 128 + row;
-    __nv_bfloat16* base = dqkv + (k_glob * h + hh) * 3 * DH;
-    store_acc_row(tmem_dK + lane_addr, base + DH);
-    store_acc_row(tmem_dV + lane_addr, base + 2 * DH);
   }
   fence_before();
   __syncthreads();
@@ -414,45 +532,42 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward dQ : CTA = (b, head, query tile i); loops over key tiles j = 0 .. i
+// backward dQ : item = (b, head, query tile i); steps = key tiles j = 0 .. i
 // ------------------------------------------------------------------------------------------------
 struct AttnDqSmem {
-  static constexpr int Q = 0, DO = AT_TILE, K = 2 * AT_TILE, V = 4 * AT_TILE, DS = 6 * AT_TILE, BAR = 8 * AT_TILE;
-  static constexpr int TOTAL = BAR + 16 * 8 + 16 + 1024;
+  static constexpr int Q = 0, DO = 2 * AT_TILE, K = 4 * AT_TILE, V = 6 * AT_TILE, DS = 8 * AT_TILE, BAR = 10 * AT_TILE;
+  static constexpr int TOTAL = BAR + 24 * 8 + 16 + 1024;
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const float* __restrict__ lse, const float* __restrict__ D, __nv_bfloat16* __restrict__ dqkv,
                    int B, int S, int h, float inv_div) {
-  constexpr int DH = 64;
+  constexpr int DH = AT_DH;
   using L = AttnDqSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
-  uint64_t *qdo_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 6,
-           *ds_full = bars + 7, *acc_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t *qdo_full = bars, *qdo_empty = bars + 2, *kv_full = bars + 4, *kv_empty = bars + 6, *s_full = bars + 8,
+           *s_empty = bars + 9, *ds_full = bars + 10, *acc_done = bars + 11, *out_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqt = S / 128;
-  const int i = nqt - 1 - (int)(blockIdx.x % nqt);
-  const int bh = blockIdx.x / nqt;
-  const int b = bh / h, hh = bh - b * h;
-  const int n_kv = i + 1;
-  const int col_q = hh * 3 * DH, col_k = col_q + DH, col_v = col_q + 2 * DH;
-  const int col_do = hh * DH;
-  const int row0 = b * S;
+  const int total = B * h * nqt;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
-    mbar_init(qdo_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(qdo_full + s, 1); mbar_init(qdo_empty + s, 1);
+      mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1);
+    }
     mbar_init(s_full, 1);
     mbar_init(s_empty, 4);
     mbar_init(ds_full, 4);
     mbar_init(acc_done, 1);
+    mbar_init(out_done, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -464,68 +579,99 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(qdo_full, 2 * AT_TILE);
-      tma_load_4d(&tmQKV, qdo_full, smem + L::Q, col_q, row0 + i * 128, 0, 0);
-      tma_load_4d(&tmDO, qdo_full, smem + L::DO, col_do, row0 + i * 128, 0, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(kv_empty + st, ((j >> 1) & 1) ^ 1);
+      Cursor c;
+      for (c.init(blockIdx.x, total, gridDim.x, nqt, true, false); c.valid(); c.next()) {
+        const int b = c.bh / h, hh = c.bh - b * h;
+        const int col_q = hh * 3 * DH, row0 = b * S;
+        if (c.first_step()) {
+          const int qb = c.wi & 1;
+          mbar_wait(qdo_empty + qb, ((c.wi >> 1) & 1) ^ 1);
+          mbar_expect_tx(qdo_full + qb, 2 * AT_TILE);
+          tma_load_4d(&tmQKV, qdo_full + qb, smem + L::Q + qb * AT_TILE, col_q, row0 + c.tile * 128, 0, 0);
+          tma_load_4d(&tmDO, qdo_full + qb, smem + L::DO + qb * AT_TILE, hh * DH, row0 + c.tile * 128, 0, 0);
+        }
+        const int st = c.t & 1;
+        mbar_wait(kv_empty + st, ((c.t >> 1) & 1) ^ 1);
         mbar_expect_tx(kv_full + st, 2 * AT_TILE);
-        tma_load_4d(&tmQKV, kv_full + st, smem + L::K + st * AT_TILE, col_k, row0 + j * 128, 0, 0);
-        tma_load_4d(&tmQKV, kv_full + st, smem + L::V + st * AT_TILE, col_v, row0 + j * 128, 0, 0);
+        tma_load_4d(&tmQKV, kv_full + st, smem + L::K + st * AT_TILE, col_q + DH, row0 + c.j * 128, 0, 0);
+        tma_load_4d(&tmQKV, kv_full + st, smem + L::V + st * AT_TILE, col_q + 2 * DH, row0 + c.j * 128, 0, 0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(128, false, false);
       constexpr uint32_t idesc_q = make_idesc(DH, false, true);  // dQ = dS K : dS K-major, K tile MN-major
-      const uint32_t sq = smem_u32(smem + L::Q), sdo = smem_u32(smem + L::DO), sds = smem_u32(smem + L::DS);
-      mbar_wait(qdo_full, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1, ph = (j >> 1) & 1;
-        const uint32_t sk = smem_u32(smem + L::K + st * AT_TILE), sv = smem_u32(smem + L::V + st * AT_TILE);
-        mbar_wait(kv_full + st, ph);
-        if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+      const uint32_t sds = smem_u32(smem + L::DS);
+      auto issue_sdp = [&](const Cursor& c) {
+        const int st = c.t & 1, qb = c.wi & 1;
+        if (c.first_step()) mbar_wait(qdo_full + qb, (c.wi >> 1) & 1);
+        mbar_wait(kv_full + st, (c.t >> 1) & 1);
+        mbar_wait(s_empty, (c.t & 1) ^ 1);
         fence_after();
-        const uint64_t dq = make_smem_desc(sq, 16, 1024), dk = make_smem_desc(sk, 16, 1024);
-        const uint64_t ddo = make_smem_desc(sdo, 16, 1024), dv = make_smem_desc(sv, 16, 1024);
+        const uint64_t dq = make_smem_desc(smem_u32(smem + L::Q + qb * AT_TILE), 16, 1024);
+        const uint64_t dk = make_smem_desc(smem_u32(smem + L::K + st * AT_TILE), 16, 1024);
+        const uint64_t ddo = make_smem_desc(smem_u32(smem + L::DO + qb * AT_TILE), 16, 1024);
+        const uint64_t dv = make_smem_desc(smem_u32(smem + L::V + st * AT_TILE), 16, 1024);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_dP, ddo + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), idesc_s, k > 0);
         umma_commit(s_full);
-        mbar_wait(ds_full, j & 1);
+      };
+      Cursor cs, ca;
+      cs.init(blockIdx.x, total, gridDim.x, nqt, true, false);
+      ca = cs;
+      if (cs.valid()) { issue_sdp(cs); cs.next(); }
+      for (; ca.valid(); ca.next()) {
+        const int st = ca.t & 1, qb = ca.wi & 1;
+        mbar_wait(ds_full, ca.t & 1);
+        if (cs.valid()) { issue_sdp(cs); cs.next(); }
+        if (ca.first_step()) mbar_wait(out_done, (ca.wi & 1) ^ 1);
         fence_after();
-        const uint64_t dkb = make_smem_desc(sk, 16384, 1024);
+        const uint64_t dkb = make_smem_desc(smem_u32(smem + L::K + st * AT_TILE), 16384, 1024);
+        const bool acc0 = !ca.first_step();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t dds = make_smem_desc(sds + (k >> 2) * 16384, 16, 1024) + (uint64_t)((k & 3) * 2);
-          umma_bf16(tmem_dQ, dds, dkb + (uint64_t)(k * 128), idesc_q, (j > 0 || k > 0));
+          umma_bf16(tmem_dQ, dds, dkb + (uint64_t)(k * 128), idesc_q, (acc0 || k > 0));
         }
         umma_commit(acc_done);
         umma_commit(kv_empty + st);
+        if (ca.last_step()) umma_commit(qdo_empty + qb);
       }
     }
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const int64_t stat = ((int64_t)b * h + hh) * S + i * 128 + row;
-    const float lse_r = lse[stat], D_r = D[stat];
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
+    const uint32_t sdS = smem_u32(smem + L::DS);
+    float lse_r = 0.f, D_r = 0.f;
+    Cursor c;
+    for (c.init(blockIdx.x, total, gridDim.x, nqt, true, false); c.valid(); c.next()) {
+      const int b = c.bh / h, hh = c.bh - b * h;
+      if (c.first_step()) {
+        const int64_t stat = ((int64_t)b * h + hh) * S + c.tile * 128 + row;
+        lse_r = lse[stat];
+        D_r = D[stat];
+      }
+      mbar_wait(s_full, c.t & 1);
       fence_after();
-      if (j > 0) mbar_wait(acc_done, (j - 1) & 1);  // previous dS tile consumed
-      bwd_rows<false>(tmem_S, tmem_dP, lane_addr, row, j == i, lse_r, D_r, inv_div, nullptr, smem + L::DS);
+      bwd_rows<false>(tmem_S + lane_addr, tmem_dP + lane_addr, row, c.last_step(), lse_r, D_r, inv_div, 0u, sdS,
+                      c.t > 0 ? acc_done : nullptr, (c.t - 1) & 1);
       fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(ds_full); }
+      if (c.last_step()) {
+        mbar_wait(acc_done, c.t & 1);
+        fence_after();
+        const int64_t q_glob = (int64_t)b * S + c.tile * 128 + row;
+        store_acc_row(tmem_dQ + lane_addr, dqkv + (q_glob * h + hh) * 3 * DH);
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(out_done);
+      }
     }
-    mbar_wait(acc_done, (n_kv - 1) & 1);
-    fence_after();
-    const int64_t q_glob = (int64_t)row0 + i * 128 + row;
-    store_acc_row(tmem_dQ + lane_addr, dqkv + (q_glob * h + hh) * 3 * DH);
   }
   fence_before();
   __syncthreads();
@@ -540,6 +686,11 @@ static int check_shape(const char* who, int B, int S, int h, int Dh) {
   NPT_REQUIRE(Dh == 64, "%s: fused attention supports head_dim 64 only (got %d); use the GEMM + softmax path", who, Dh);
   NPT_REQUIRE(S > 0 && S % 128 == 0, "%s: fused attention needs seq_len %% 128 == 0 (got %d)", who, S);
   return 0;
+}
+
+static int persistent_grid(int items) {
+  const int sms = sm_count();
+  return items < sms ? items : sms;
 }
 
 }  // namespace npt
@@ -561,7 +712,7 @@ int npt_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int32_t 
     NPT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::TOTAL));
     attr = true;
   }
-  const int grid = B * h * (S / 128);
+  const int grid = persistent_grid(B * h * (S / 128));
   attn_fwd_kernel<<<grid, AT_THREADS, AttnFwdSmem::TOTAL, (cudaStream_t)stream>>>(
       tm, (__nv_bfloat16*)out_bf16, lse, B, S, h, 1.0f / divisor);
   NPT_LAUNCH_CHECK();
@@ -592,7 +743,7 @@ int npt_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_
     NPT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem::TOTAL));
     attr = true;
   }
-  const int grid = B * h * (S / 128);
+  const int grid = persistent_grid(B * h * (S / 128));
   const float inv_div = 1.0f / divisor;
   attn_bwd_dkv_kernel<<<grid, AT_THREADS, AttnDkvSmem::TOTAL, st>>>(tmQKV, tmDO, lse, D, (__nv_bfloat16*)dqkv_bf16, B, S, h, inv_div);
   NPT_LAUNCH_CHECK();

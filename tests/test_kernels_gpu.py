@@ -210,7 +210,10 @@ def test_gemm_batched_head_layout(mode):
     assert not got[:, :, :, 0, :].any() and not got[:, :, :, 2, :].any()
 
 
-@pytest.mark.parametrize("B,S,h", [(1, 128, 1), (2, 256, 3), (1, 512, 2), (3, 256, 6)])
+@pytest.mark.parametrize("B,S,h", [(1, 128, 1), (2, 256, 3), (1, 512, 2), (3, 256, 6),
+                                   (40, 256, 6),     # 480 work items: every persistent CTA walks several
+                                   (50, 128, 4),     # 200 single-step items
+                                   (13, 384, 5)])    # 195 items of 1-3 steps
 def test_fused_attention_fwd_bwd(B, S, h):
     """Flash-style tcgen05 attention against the reference's arithmetic (attention.py:43-52, 81-98)
     evaluated in fp64 on the same bf16-rounded inputs; scale = 1/sqrt(d_model) with d_model = 384."""
