@@ -30,6 +30,10 @@ const char* npt_last_error(void);
 int npt_version(void);
 /* Number of kernel launches this library has issued in this process (monotonic). */
 unsigned long long npt_launch_count(void);
+/* Number of SMs the persistent GEMM grids leave free from now on (0 = use all).  The tensor-parallel
+ * backward raises it while an NCCL all-reduce (distributed/all_reduce.py:23) is in flight on another
+ * stream, so the collective's CTAs can be scheduled next to the dW GEMM. */
+int npt_set_sm_margin(int32_t sms);
 /* Fills SM count and compute capability of the current device. */
 int npt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

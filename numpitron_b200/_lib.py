@@ -53,6 +53,7 @@ _SIGNATURES = {
     "npt_last_error": (C.c_char_p, []),
     "npt_version": (c_int, []),
     "npt_launch_count": (C.c_ulonglong, []),
+    "npt_set_sm_margin": (c_int, [c_int32]),
     "npt_device_info": (c_int, [C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
     "npt_pinned_alloc": (c_int, [C.POINTER(c_void_p), c_size_t]),
     "npt_pinned_free": (c_int, [_P]),

@@ -40,6 +40,7 @@ constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 
 int sm_count();
+int sm_margin();  // SMs persistent GEMMs leave free while a collective overlaps them
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

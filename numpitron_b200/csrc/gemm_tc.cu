@@ -584,7 +584,8 @@ static int launch_tc(const TcParams& p, const GemmEpilogue& epi, float* partial,
     NPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  int grid = sm_count();
+  int grid = sm_count() - sm_margin();
+  if (grid < 1) grid = 1;
   if (grid > p.total_tiles) grid = p.total_tiles;
   kern<<<grid, TC_THREADS, L::TOTAL, st>>>(tmA, tmB, tmC, tmCb, p, epi, partial);
   NPT_LAUNCH_CHECK();

@@ -30,9 +30,19 @@ int sm_count() {
   return cached;
 }
 
+static int g_sm_margin = 0;
+int sm_margin() { return g_sm_margin; }
+
 }  // namespace npt
 
 extern "C" {
+
+// SMs that persistent GEMM grids leave free (for a collective that is in flight on another stream).
+int npt_set_sm_margin(int32_t sms) {
+  NPT_REQUIRE(sms >= 0 && sms < 128, "set_sm_margin: out of range");
+  npt::g_sm_margin = sms;
+  return 0;
+}
 
 const char* npt_last_error(void) { return npt::g_err; }
 

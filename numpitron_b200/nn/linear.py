@@ -1,8 +1,15 @@
 """Linear — drop-in for the reference's nn/linear.py (same constructor, forward, backward)."""
 from __future__ import annotations
 
+import os
+
+from .. import ops
 from . import functional as F
 from .core import Layer, weight_init_fn
+
+# SMs the dW GEMM leaves free while the tensor-parallel all-reduce of dX is in flight.  Measured on
+# 2 x B200 (profiles/README.md): 0, 16 and 32 give the same step time, so the default is 0.
+TP_OVERLAP_SM_MARGIN = int(os.environ.get("NUMPITRON_TP_SM_MARGIN", "0"))
 
 
 class Linear(Layer):
@@ -34,9 +41,14 @@ class Linear(Layer):
         start their all-reduce there so it overlaps the dW / db kernels."""
         inputs = self.ctx.pop("inputs")
         d_in = F.linear_backward_input(d_out, self, "weight", mask=mask, out=out)
+        margin = TP_OVERLAP_SM_MARGIN if on_dx is not None else 0
         if on_dx is not None:
             on_dx(d_in)
+        if margin:
+            ops.set_sm_margin(margin)  # leave SMs for the all-reduce next to the dW GEMM
         self.update_parameter("weight", gradient=F.linear_backward_weight(inputs, d_out))
         if self.use_bias:
             self.update_parameter("bias", gradient=F.bias_grad(d_out))
+        if margin:
+            ops.set_sm_margin(0)
         return d_in

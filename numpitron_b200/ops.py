@@ -24,6 +24,11 @@ def _p(t, off=0):
     return rt.ptr(t, off)
 
 
+def set_sm_margin(sms: int) -> None:
+    """Leave `sms` SMs out of the persistent GEMM grids (room for an in-flight NCCL collective)."""
+    check(_lib_().npt_set_sm_margin(int(sms)), "npt_set_sm_margin")
+
+
 # ---- GEMM ----------------------------------------------------------------------------------------
 def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_off=0,
          a_strides=(0, 0), b_strides=(0, 0), C_out=None, ldc=0, c_off=0, c_strides=(0, 0),

@@ -87,3 +87,14 @@ def test_compute_refuses_to_run_without_gpu():
     ln = LayerNorm(32, rng=np.random.default_rng(0))
     with pytest.raises(_lib.NptError, match="no CPU fallback"):
         ln(np.zeros((1, 2, 32), np.float32))
+
+
+def test_token_ids_must_fit_uint16():
+    import numpy as np
+
+    from numpitron_b200.nn.core import _host_to_device
+
+    with pytest.raises(ValueError, match="uint16"):
+        _host_to_device(np.array([[0, 70000]], dtype=np.int64))
+    with pytest.raises(ValueError, match="uint16"):
+        _host_to_device(np.array([[-1, 3]], dtype=np.int64))

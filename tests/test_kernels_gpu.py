@@ -446,3 +446,44 @@ def test_adam_multi_tensor_bit_exact_vs_oracle():
             got = host(sh)
             np.testing.assert_array_equal(got[:, : p.shape[1]], bf16_round(p2))
             assert not got[:, p.shape[1]:].any()
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: empty inputs, the uint16 token range, error reporting through the C ABI
+# ---------------------------------------------------------------------------------------------
+def test_empty_inputs_are_noops():
+    lib = __import__("numpitron_b200._lib", fromlist=["load"]).load()
+    st = rt.stream()
+    assert lib.npt_layernorm_fwd(None, None, None, None, None, None, None, None, 0, 384, 1e-5, st) == 0
+    assert lib.npt_relu_fwd(None, None, None, 0, st) == 0
+    assert lib.npt_embedding_gather(None, None, 65, None, None, None, 0, 256, 384, 0, 64, 1, st) == 0
+    assert lib.npt_cast_f32_bf16(None, 8, None, 8, 0, 8, st) == 0
+
+
+def test_full_uint16_vocabulary_and_single_token():
+    """V = 65536 (every uint16 value is a valid token, incl. 65535), T = 1 and T = 3."""
+    rng = np.random.default_rng(1)
+    V, d = 65536, 16
+    E = rng.standard_normal((d, V)).astype(np.float32)
+    for toks in ([65535], [0, 65535, 65535]):
+        tokens = np.array([toks], dtype=np.uint16)
+        T = tokens.size
+        d_out = rng.standard_normal((1, T, d)).astype(np.float32)
+        y_ref, ctx = O.embedding_forward(tokens.copy(), E, 0, V, True)
+        g_ref = O.embedding_backward(ctx, np.zeros_like(E), d_out)
+        np.testing.assert_array_equal(host(ops.embedding_gather(dev(tokens), dev(E), None, T, 0, V, True)), y_ref)
+        grad = rt.zeros((d, V))
+        ops.embedding_scatter_add(dev(tokens), dev(d_out), grad, 0, V, True)
+        np.testing.assert_array_equal(host(grad), g_ref)
+
+
+def test_errors_are_reported_not_swallowed():
+    from numpitron_b200._lib import NptError
+
+    a = rt.empty((128, 64), torch.bfloat16)
+    with pytest.raises(NptError, match="multiples of 8"):
+        ops.gemm(a, a, 128, 60, 64, lda=64, ldb=60, C_out=rt.empty((128, 60)), ldc=60, mode=1)  # ldb % 8 != 0
+    with pytest.raises(TypeError):
+        ops.gemm(a, a, 128, 64, 64, lda=64, ldb=64, C_out=rt.empty((128, 64)), ldc=64, mode=0)  # bf16 into the fp32 kernel
+    with pytest.raises(NptError, match="head_dim 64"):
+        ops.attention_fwd(rt.empty((1, 128, 3 * 96), torch.bfloat16), 1, 128, 1, 96, 10.0)
