@@ -19,6 +19,7 @@
 // tile i+1.  Split-K partials go to a workspace (also by TMA store) and are reduced in fixed
 // order by gemm.cu (deterministic).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gemm_common.cuh"
 
@@ -61,6 +62,28 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// Multicast form: the box lands at the same shared-memory offset in every CTA of `mask`, and the
+// bytes are credited to the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6, %7}], [%2], %3;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -168,7 +191,10 @@ struct TcParams {
   int raw;        // 1: split-K partial (no epilogue math), stored through map C as {N, M, batch, split}
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// CL = 2: CTA pairs (thread-block clusters) work on two vertically adjacent tiles (m, n) / (m+1, n);
+// each CTA fetches half of the shared B tile and TMA-multicasts it into both CTAs' shared memory,
+// which halves the L2 -> SM traffic of the weight operand (the dominant term when M >> N).
+template <int BN, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCb,
@@ -195,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full_bar + s, 1);
-      mbar_init(empty_bar + s, 1);
+      mbar_init(empty_bar + s, CL);  // every CTA of the cluster must have consumed the stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar + a, 1);
@@ -206,15 +232,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_alloc<L::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync();  // peers' barriers are initialised before any multicast reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int cta_rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  // work units: one tile (CL = 1) or one vertical pair of tiles (CL = 2) per step of the persistent loop
+  const int unit_first = blockIdx.x / CL, unit_stride = gridDim.x / CL, units = p.total_tiles / CL;
 
   // tile -> (n_tile fastest, m_tile, z = batch*splits)
   auto decode = [&](int t, int& m0, int& n0, int& b, int& split, int& bi, int& bo, int& kb_begin, int& nkb) {
     const int nt = t % p.n_tiles;
     const int r = t / p.n_tiles;
-    const int mt = r % p.m_tiles;
-    const int z = r / p.m_tiles;
+    const int mrows = p.m_tiles / CL;          // rows of units
+    const int mt = (r % mrows) * CL + cta_rank;
+    const int z = r / mrows;
     b = z / p.splits;
     split = z - b * p.splits;
     bo = b / epi.batch_inner;
@@ -231,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t it = 0;  // running k-block counter across tiles
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = unit_first; t < units; t += unit_stride) {
         int m0, n0, b, split, bi, bo, kb_begin, nkb;
         decode(t, m0, n0, b, split, bi, bo, kb_begin, nkb);
         for (int i = 0; i < nkb; ++i, ++it) {
@@ -247,7 +278,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             tma_load_4d(&tmA, full_bar + s, sa, k0, m0, bi, bo);
           }
-          if (B_MN) {
+          if (CL > 1) {
+            // this CTA fetches its half of the B tile and multicasts it to both CTAs of the pair
+            if (B_MN) {  // boxes {64 n, 32 k}: k rows [rank*32, rank*32+32) of every 64-wide n chunk
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_4d_mc(&tmB, full_bar + s, sb + c * 64 * TC_BK * 2 + cta_rank * 32 * 128, n0 + c * 64,
+                               k0 + cta_rank * 32, bi, bo, (uint16_t)3);
+            } else {     // box {64 k, BN/2 n}: n rows [rank*BN/2, ...)
+              tma_load_4d_mc(&tmB, full_bar + s, sb + cta_rank * (BN / 2) * 128, k0, n0 + cta_rank * (BN / 2), bi, bo,
+                             (uint16_t)3);
+            }
+          } else if (B_MN) {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
               tma_load_4d(&tmB, full_bar + s, sb + c * 64 * TC_BK * 2, n0 + c * 64, k0, bi, bo);
@@ -262,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
       uint32_t it = 0, tile_i = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_i) {
+      for (int t = unit_first; t < units; t += unit_stride, ++tile_i) {
         int m0, n0, b, split, bi, bo, kb_begin, nkb;
         decode(t, m0, n0, b, split, bi, bo, kb_begin, nkb);
         const uint32_t acc = tile_i & 1;
@@ -282,7 +324,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
             umma_bf16(d_tmem, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc, (i > 0 || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar + s);  // frees this smem stage once the MMAs above retire
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
+          if (CL > 1) umma_commit_mc(empty_bar + s, (uint16_t)3); else umma_commit(empty_bar + s);
         }
         umma_commit(tmem_full_bar + acc);  // accumulator complete
       }
@@ -295,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool want_bf16 = !p.raw && epi.Cb != nullptr;
     const bool masked = !p.raw && epi.mask != nullptr;
     uint32_t tile_i = 0, store_i = 0;  // store_i counts committed TMA-store groups (staging buffer parity)
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_i) {
+    for (int t = unit_first; t < units; t += unit_stride, ++tile_i) {
       int m0, n0, b, split, bi, bo, kb_begin, nkb;
       decode(t, m0, n0, b, split, bi, bo, kb_begin, nkb);
       const uint32_t acc = tile_i & 1;
@@ -418,6 +461,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             epi.bits_out[(int64_t)m * epi.ld_bits + (nb >> 5)] = w;
           }
         }
+        // two staging slots per warp (a deeper ring — 3 fp32 / 6 bf16 slots — was measured: no gain)
         const uint32_t bufsel = store_i & 1;
         ++store_i;
         uint8_t* s32 = stage_base + bufsel * L::EPI_F32;
@@ -487,6 +531,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync();  // no CTA leaves while its peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<L::TMEM_COLS>(tmem_base);
@@ -574,11 +619,11 @@ int gemm_tc_splits(const npt_gemm_args& a) {
   return (int)cdiv(kblocks, kps);  // no empty split
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_tc(const TcParams& p, const GemmEpilogue& epi, float* partial, const CUtensorMap& tmA,
-                     const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCb, cudaStream_t st) {
+template <int BN, bool A_MN, bool B_MN, int CL>
+static int launch_tc_cl(const TcParams& p, const GemmEpilogue& epi, float* partial, const CUtensorMap& tmA,
+                        const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCb, cudaStream_t st) {
   using L = TcSmem<BN>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     NPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -587,9 +632,46 @@ static int launch_tc(const TcParams& p, const GemmEpilogue& epi, float* partial,
   int grid = sm_count() - sm_margin();
   if (grid < 1) grid = 1;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  kern<<<grid, TC_THREADS, L::TOTAL, st>>>(tmA, tmB, tmC, tmCb, p, epi, partial);
+  if (CL == 1) {
+    kern<<<grid, TC_THREADS, L::TOTAL, st>>>(tmA, tmB, tmC, tmCb, p, epi, partial);
+  } else {
+    grid -= grid % CL;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmCb, p, epi, partial));
+  }
   NPT_LAUNCH_CHECK();
   return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const TcParams& p, const GemmEpilogue& epi, float* partial, const CUtensorMap& tmA,
+                     const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCb, int cl, cudaStream_t st) {
+  if (cl == 2) return launch_tc_cl<BN, A_MN, B_MN, 2>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
+  return launch_tc_cl<BN, A_MN, B_MN, 1>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
+}
+
+// CTA pairs with a multicast B tile.  MEASURED (profiles/README.md): on B200 a 2-CTA multicast does not
+// lower the time of these GEMMs (16384x1536x384: 40.0 us vs 39.0 us without; 8192^3: 907 vs 927 us) —
+// consistent with the microarchitecture notes (multicast ~ unicast for clusters <= 4) — so the path
+// is OFF by default and kept, tested, behind NUMPITRON_GEMM_CLUSTER=1 for larger-cluster work.
+static int tc_cluster(const npt_gemm_args& a, int bn, int splits) {
+  const char* on = getenv("NUMPITRON_GEMM_CLUSTER");
+  if (!on || on[0] != '1' || bn < 128) return 1;
+  const int64_t m_tiles = cdiv(a.M, TC_BM);
+  if (m_tiles % 2 != 0) return 1;
+  const int64_t units = m_tiles / 2 * cdiv(a.N, bn) * a.batch * splits;
+  return units >= sm_count() / 2 ? 2 : 1;
 }
 
 int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, float* partial, cudaStream_t st) {
@@ -602,8 +684,9 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
   if (a.trans_a) rc = make_map_bf16(&tmA, a.A, a.M, a.K, a.lda, n_bi, a.stride_a_inner, n_bo, a.stride_a_outer, 64, 64);
   else           rc = make_map_bf16(&tmA, a.A, a.K, a.M, a.lda, n_bi, a.stride_a_inner, n_bo, a.stride_a_outer, 64, TC_BM);
   if (rc) return rc;
-  if (a.trans_b) rc = make_map_bf16(&tmB, a.B, a.K, a.N, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, bn);
-  else           rc = make_map_bf16(&tmB, a.B, a.N, a.K, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, 64);
+  const int cl = tc_cluster(a, bn, splits);  // 2: each CTA of a pair loads half of the B tile (multicast)
+  if (a.trans_b) rc = make_map_bf16(&tmB, a.B, a.K, a.N, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, bn / cl);
+  else           rc = make_map_bf16(&tmB, a.B, a.N, a.K, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, 64 / cl);
   if (rc) return rc;
 
   TcParams p;
@@ -645,10 +728,10 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
   }
   const bool a_mn = a.trans_a != 0, b_mn = a.trans_b == 0;
 #define NPT_TC_CASE(BNV)                                                                            \
-  if (a_mn && b_mn) return launch_tc<BNV, true, true>(p, epi, partial, tmA, tmB, tmC, tmCb, st);     \
-  if (a_mn && !b_mn) return launch_tc<BNV, true, false>(p, epi, partial, tmA, tmB, tmC, tmCb, st);   \
-  if (!a_mn && b_mn) return launch_tc<BNV, false, true>(p, epi, partial, tmA, tmB, tmC, tmCb, st);   \
-  return launch_tc<BNV, false, false>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
+  if (a_mn && b_mn) return launch_tc<BNV, true, true>(p, epi, partial, tmA, tmB, tmC, tmCb, cl, st);     \
+  if (a_mn && !b_mn) return launch_tc<BNV, true, false>(p, epi, partial, tmA, tmB, tmC, tmCb, cl, st);   \
+  if (!a_mn && b_mn) return launch_tc<BNV, false, true>(p, epi, partial, tmA, tmB, tmC, tmCb, cl, st);   \
+  return launch_tc<BNV, false, false>(p, epi, partial, tmA, tmB, tmC, tmCb, cl, st);
   if (bn == 64) { NPT_TC_CASE(64) }
   if (bn == 192) { NPT_TC_CASE(192) }
   if (bn == 256) { NPT_TC_CASE(256) }

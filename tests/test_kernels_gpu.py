@@ -142,6 +142,24 @@ def test_gemm_bf16_persistent_many_tiles_and_fused_epilogues():
     np.testing.assert_array_equal(host(dxb2), host(dxb))
 
 
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(16384, 384, 200), (9984, 1152, 136), (16384, 1536, 72), (20480, 128, 320)])
+def test_gemm_bf16_cta_pairs_multicast(M, N, K, ta, tb, monkeypatch):
+    """Shapes large enough for the 2-CTA cluster path (B tile fetched half by each CTA and TMA-multicast
+    to both), all four operand layouts, BN = 128 / 192 / 256, ragged K tails.  The path is opt-in
+    (NUMPITRON_GEMM_CLUSTER=1, read at every launch)."""
+    monkeypatch.setenv("NUMPITRON_GEMM_CLUSTER", "1")
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn((K, M) if ta else (M, K), device="cuda", generator=g).bfloat16()
+    b = torch.randn((N, K) if tb else (K, N), device="cuda", generator=g).bfloat16()
+    c = rt.empty((M, N))
+    ops.gemm(a, b, M, N, K, lda=a.shape[1], ldb=b.shape[1], trans_a=ta, trans_b=tb, C_out=c, ldc=N, mode=1)
+    ref = (a.double().T if ta else a.double()) @ (b.double().T if tb else b.double())
+    torch.cuda.synchronize()
+    err = (c.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err
+
+
 @pytest.mark.parametrize("M,K,N", [(16384, 384, 1536), (300, 136, 200), (128, 64, 72)])
 def test_gemm_packed_relu_bits(M, K, N):
     """The forward epilogue packs (relu output > 0) into 1 bit/element; the backward GEMM consuming those
