@@ -24,6 +24,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
          "-Xptxas", "-v" if os.environ.get("NPT_PTXAS_V") else "-O3"]
+FLAGS += os.environ.get("NPT_NVCC_EXTRA", "").split()  # e.g. -DNPT_GEMM_DEBUG for the timing experiments
 
 
 def sources():
