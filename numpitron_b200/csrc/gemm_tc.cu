@@ -103,17 +103,45 @@ int gemm_tc_splits(const npt_gemm_args& a) {
   return (int)cdiv(kblocks, kps);  // no empty split
 }
 
-// CTA pairs with a multicast B tile.  MEASURED (profiles/README.md): on B200 a 2-CTA multicast does not
-// lower the time of these GEMMs (16384x1536x384: 40.0 us vs 39.0 us without; 8192^3: 907 vs 927 us) —
-// consistent with the microarchitecture notes (multicast ~ unicast for clusters <= 4) — so the path
-// is OFF by default and kept, tested, behind NUMPITRON_GEMM_CLUSTER=1 for larger-cluster work.
-static int tc_cluster(const npt_gemm_args& a, int bn, int splits) {
-  const char* on = getenv("NUMPITRON_GEMM_CLUSTER");
-  if (!on || on[0] != '1' || bn < 128) return 1;
+// Can this launch use the fast epilogue (gemm_tc_kernel.cuh)?  One output kind, written by TMA, no
+// tensor mask, bias readable 16 bytes at a time.
+static bool tc_fast_ok(const npt_gemm_args& a) {
+  if (a.mask || (a.C != nullptr) == (a.C_bf16 != nullptr)) return false;
+  if (a.bias && !aligned16(a.bias)) return false;
+  if (a.C) return aligned16(a.C) && a.ldc % 4 == 0 && a.stride_c_outer % 4 == 0 && a.stride_c_inner % 4 == 0;
+  return aligned16(a.C_bf16) && a.ldcb % 8 == 0 && a.stride_cb_outer % 8 == 0 && a.stride_cb_inner % 8 == 0;
+}
+
+// Tile width and CTA grouping of a launch without split-K.  Model: the launch takes
+// waves x (time of one k-block), where a k-block costs the larger of its MMA time (~2.3 cycles per
+// tile column) and its shared-memory fill time at ~64 B/clk (128 rows of A + BN / cl rows of B, 128
+// bytes each); a CTA pair (cl = 2, tcgen05 cta_group::2) halves the B rows each SM has to pull in.
+// NUMPITRON_GEMM_PAIR=0 turns the pairs off (A/B comparison in the microbenchmarks).
+struct TcConfig { int bn, cl; };
+static TcConfig tc_config(const npt_gemm_args& a) {
+  TcConfig best = {tc_bn(a), 1};
   const int64_t m_tiles = cdiv(a.M, TC_BM);
-  if (m_tiles % 2 != 0) return 1;
-  const int64_t units = m_tiles / 2 * cdiv(a.N, bn) * a.batch * splits;
-  return units >= sm_count() / 2 ? 2 : 1;
+  const int sms = sm_count();
+  // measured (profiles/README.md): pairs win from N ~ 1024 up (16384x1536x384: 24.3 vs 26.8 us, 8192^3: 756 vs
+  // 925 us) and lose on narrow outputs, where a launch is a couple of tiles per CTA and fixed costs dominate
+  if (a.N < 1024 || m_tiles % 2 != 0 || !tc_fast_ok(a)) return best;
+  if (m_tiles * cdiv(a.N, best.bn) * a.batch * 2 <= sms) return best;  // split-K territory: single CTAs
+  const char* env = getenv("NUMPITRON_GEMM_PAIR");
+  if (env && env[0] == '0') return best;
+  auto cost = [&](int bn, int cl) {
+    const int64_t units = m_tiles / cl * cdiv(a.N, bn) * a.batch;
+    const int64_t waves = cdiv(units, (int64_t)(sms / cl));
+    const double mma = 2.3 * bn, fill = 2.0 * (128 + bn / cl);
+    return (double)waves * (mma > fill ? mma : fill);
+  };
+  double best_cost = cost(best.bn, 1);
+  const int cand[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    if (cand[i] == 192 && !a.trans_b) continue;  // half of a 192-wide MN-major B tile is not a whole 64-column box
+    const double c = cost(cand[i], 2);
+    if (c < best_cost * 0.97) { best_cost = c; best.bn = cand[i]; best.cl = 2; }
+  }
+  return best;
 }
 
 #ifdef NPT_GEMM_DEBUG
@@ -132,7 +160,9 @@ NPT_TC_EXTERN(64) NPT_TC_EXTERN(128) NPT_TC_EXTERN(192) NPT_TC_EXTERN(256)
 #undef NPT_TC_EXTERN
 
 int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, float* partial, cudaStream_t st) {
-  const int bn = tc_bn(a);
+  TcConfig cfg = {tc_bn(a), 1};
+  if (splits == 1) cfg = tc_config(a);
+  const int bn = cfg.bn, cl = cfg.cl;
   const int64_t n_bi = a.batch_inner, n_bo = cdiv(a.batch, a.batch_inner);
   CUtensorMap tmA, tmB, tmC, tmCb;
   memset(&tmC, 0, sizeof(tmC));
@@ -141,9 +171,9 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
   if (a.trans_a) rc = make_map_bf16(&tmA, a.A, a.M, a.K, a.lda, n_bi, a.stride_a_inner, n_bo, a.stride_a_outer, 64, 64);
   else           rc = make_map_bf16(&tmA, a.A, a.K, a.M, a.lda, n_bi, a.stride_a_inner, n_bo, a.stride_a_outer, 64, TC_BM);
   if (rc) return rc;
-  const int cl = tc_cluster(a, bn, splits);  // 2: each CTA of a pair loads half of the B tile (multicast)
+  // B: one box of bn / cl rows (K-major), or 64 x 64 boxes (MN-major); a CTA of a pair loads half of the tile
   if (a.trans_b) rc = make_map_bf16(&tmB, a.B, a.K, a.N, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, bn / cl);
-  else           rc = make_map_bf16(&tmB, a.B, a.N, a.K, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, 64 / cl);
+  else           rc = make_map_bf16(&tmB, a.B, a.N, a.K, a.ldb, n_bi, a.stride_b_inner, n_bo, a.stride_b_outer, 64, 64);
   if (rc) return rc;
 
   TcParams p;
@@ -172,7 +202,7 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
   int kind = EPI_GENERAL;
   if (p.raw) {
     p.tma_store = (a.N % 4 == 0) && aligned16(partial);
-    if (p.tma_store && cl == 1) kind = EPI_F32;
+    if (p.tma_store) kind = EPI_F32;
     if (p.tma_store) {
       rc = make_map(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B, partial, a.N, a.M, a.N, a.batch,
                     (int64_t)a.M * a.N, splits, (int64_t)a.batch * a.M * a.N, 32, 32);
@@ -190,8 +220,7 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
                     a.stride_c_inner, n_bo, a.stride_c_outer, 32, 32);
       if (rc) return rc;
     }
-    // fast epilogue: one output kind, no tensor mask, 1-CTA launch (see gemm_tc_kernel.cuh)
-    if (p.tma_store && cl == 1 && !a.mask && ((a.C != nullptr) != (a.C_bf16 != nullptr)) && (!a.bias || aligned16(a.bias))) {
+    if (tc_fast_ok(a)) {
       const int flags = (a.C ? EPI_F32 : EPI_BF16) | (a.alpha != 1.f ? EPI_ALPHA : 0) | (a.bias ? EPI_BIAS : 0) |
                         (a.relu ? EPI_RELU : 0) | (a.mask_bits ? EPI_BITS_IN : 0) | (a.relu_bits_out ? EPI_BITS_OUT : 0);
       kind = tc_epi_kind(flags);
@@ -206,6 +235,7 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
       if (rc) return rc;
     }
   }
+  NPT_REQUIRE(cl == 1 || kind != EPI_GENERAL, "gemm(tc): internal error, CTA pairs need the fast epilogue");
   const bool a_mn = a.trans_a != 0, b_mn = a.trans_b == 0;
   if (bn == 64) return launch_tc_bn<64>(p, epi, partial, tmA, tmB, tmC, tmCb, a_mn, b_mn, cl, kind, st);
   if (bn == 192) return launch_tc_bn<192>(p, epi, partial, tmA, tmB, tmC, tmCb, a_mn, b_mn, cl, kind, st);

@@ -48,19 +48,28 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-// Multicast form: the box lands at the same shared-memory offset in every CTA of `mask`, and the
-// bytes are credited to the mbarrier at the same offset in each of them.
-__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3,
-                                               uint16_t mask) {
+// CTA-pair form (cta_group::2): the box lands in THIS CTA's shared memory, the bytes are credited to
+// the mbarrier at the same offset in the pair's leader (the even-ranked CTA): clearing bit 24 of a
+// shared::cluster address selects the leader's copy.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%4, %5, %6, %7}], [%2], %3;"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+// arrives (once the MMAs issued so far retire) on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// plain arrive on the mbarrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(rank) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -83,20 +92,36 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
-template <int COLS>
+// CL = 2: one warp of EACH CTA of the pair executes these (same warp index, same dst offset)
+template <int COLS, int CL>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (CL == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
 }
-template <int COLS>
+template <int COLS, int CL>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+  if (CL == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+  else         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// CTA-pair MMA: M = 256 (128 rows from each CTA's A tile), N columns of B split between the two
+// CTAs' shared memory, the accumulator rows in each CTA's own TMEM.  Issued by the leader only.
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -154,22 +179,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M=128, N=BN.
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+// Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M = 128 (one CTA) or
+// 256 (CTA pair), N = BN.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
   return (1u << 4)                       // c_format = F32
          | (1u << 7) | (1u << 10)        // a_format = b_format = BF16
          | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
-         | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+         | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN>
+// CL = 2 (CTA pair, cta_group::2): each CTA stages its own 128 rows of A and HALF of the B tile.
+template <int BN, int CL>
 struct TcSmem {
-  // smem budget: ~178 KB of pipeline stages next to 48 KB of epilogue staging
-  static constexpr int STAGES = BN >= 256 ? 3 : BN >= 192 ? 4 : BN >= 128 ? 5 : 6;
   static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;  // power of two >= 2*BN
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
-  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int B_BYTES = (BN / CL) * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // smem budget: 227 KB - 64 KB of epilogue staging - barriers / alignment slack
+  static constexpr int STAGES_FIT = (232448 - 65536 - 1024 - 256) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;  // CL=1: 3/4/5/6 for BN = 256/192/128/64
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   // general epilogue, per warp (4 warps): 2 x (32 rows x 128 B) fp32 staging + 2 x (32 rows x 64 B) bf16 staging
   static constexpr int EPI_F32 = 32 * 128, EPI_BF16 = 32 * 64;
@@ -181,6 +209,32 @@ struct TcSmem {
   static constexpr int EPI_OFFSET = PIPE_BYTES;
   static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+};
+
+// Position of a role's current work unit; see `decode` in the kernel.
+struct TileCursor {
+  int nt, mr, z;          // n tile, row of units, batch*split index
+  int d_nt, d_mr, d_z;    // what one stride adds
+  int n_tiles, mrows;
+  int zc, b, split, bo, bi;  // cached decomposition of z
+  __device__ __forceinline__ void init(int first, int stride, int n_tiles_, int mrows_) {
+    n_tiles = n_tiles_; mrows = mrows_;
+    nt = first % n_tiles;
+    const int r = first / n_tiles;
+    mr = r % mrows; z = r / mrows;
+    d_nt = stride % n_tiles;
+    const int dr = stride / n_tiles;
+    d_mr = dr % mrows; d_z = dr / mrows;
+    zc = -1; b = split = bo = bi = 0;
+  }
+  __device__ __forceinline__ void next() {
+    nt += d_nt;
+    const int carry = nt >= n_tiles ? 1 : 0;
+    nt -= carry ? n_tiles : 0;
+    mr += d_mr + carry;
+    z += d_z;
+    if (mr >= mrows) { mr -= mrows; ++z; }
+  }
 };
 
 struct TcParams {
@@ -201,9 +255,14 @@ struct TcParams {
 #define NPT_TRACE(p, slot) do { } while (0)
 #endif
 
-// CL = 2: CTA pairs (thread-block clusters) work on two vertically adjacent tiles (m, n) / (m+1, n);
-// each CTA fetches half of the shared B tile and TMA-multicasts it into both CTAs' shared memory,
-// which halves the L2 -> SM traffic of the weight operand (the dominant term when M >> N).
+// CL = 2: CTA pairs (2-CTA clusters, tcgen05 cta_group::2) work on two vertically adjacent tiles
+// (m, n) / (m+1, n) as ONE 256 x BN MMA: each CTA stages its own 128 rows of A and half of the B
+// tile, the pair's leader (even rank) issues the MMAs, each CTA's TMEM receives its own 128 rows of
+// the accumulator and each CTA runs its own epilogue.  What this buys is shared-memory fill
+// bandwidth: a 1-CTA 128x256 tile needs 48 KB per 64-deep k-block, ~750 cycles of the SM's
+// ~64 B/clk L2->SM port against ~590 cycles of MMA (measured: loads alone 0.375 us / k-block, MMAs
+// alone 0.31 us); as a pair each CTA needs 32 KB (~500 cycles), so the tensor pipe is the limit.
+// (A 2-CTA TMA multicast of B was tried first and does not help: the bytes still enter both SMs.)
 //
 // EPI selects the epilogue.  EPI_GENERAL (6 warps) handles everything: direct stores for outputs TMA
 // cannot address, tensor ReLU masks, fp32 + bf16 outputs at once.  Every other value is the fast
@@ -226,7 +285,8 @@ __global__ void __launch_bounds__(EPI == EPI_GENERAL ? TC_THREADS : TC_THREADS_F
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCb,
                const TcParams p, const GemmEpilogue epi, float* __restrict__ partial) {
-  using L = TcSmem<BN>;
+  static_assert(CL == 1 || EPI != EPI_GENERAL, "CTA pairs run the fast epilogue only");
+  using L = TcSmem<BN, CL>;
   constexpr int TC_STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -249,18 +309,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full_bar + s, 1);
-      mbar_init(empty_bar + s, CL);  // every CTA of the cluster must have consumed the stage
+      mbar_init(empty_bar + s, 1);   // one commit (CL = 2: the leader's, delivered to both CTAs)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar + a, 1);
-      mbar_init(tmem_empty_bar + a, EPI == EPI_GENERAL ? 4 : 8);  // one arrive per epilogue warp
+      mbar_init(tmem_empty_bar + a, (EPI == EPI_GENERAL ? 4 : 8) * CL);  // one arrive per epilogue warp (of the pair)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<L::TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc<L::TMEM_COLS, CL>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync();  // peers' barriers are initialised before any multicast reaches them
+  if (CL > 1) cluster_sync();  // the peer's barriers are initialised before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) NPT_TRACE(p, 1);
@@ -268,60 +328,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // work units: one tile (CL = 1) or one vertical pair of tiles (CL = 2) per step of the persistent loop
   const int unit_first = blockIdx.x / CL, unit_stride = gridDim.x / CL, units = p.total_tiles / CL;
 
-  // tile -> (n_tile fastest, m_tile, z = batch*splits)
-  auto decode = [&](int t, int& m0, int& n0, int& b, int& split, int& bi, int& bo, int& kb_begin, int& nkb) {
-    const int nt = t % p.n_tiles;
-    const int r = t / p.n_tiles;
-    const int mrows = p.m_tiles / CL;          // rows of units
-    const int mt = (r % mrows) * CL + cta_rank;
-    const int z = r / mrows;
-    b = z / p.splits;
-    split = z - b * p.splits;
-    bo = b / epi.batch_inner;
-    bi = b - bo * epi.batch_inner;
-    m0 = mt * TC_BM;
-    n0 = nt * BN;
+  // unit -> (n_tile fastest, row of units, z = batch*splits).  Every role walks the same sequence
+  // t = unit_first, unit_first + unit_stride, ...; the cursor advances by additions only — integer
+  // divisions by run-time values cost a single thread hundreds of cycles per tile, which showed up
+  // as ~700 idle cycles of the MMA issuer between tiles in the clock64() trace.
+  auto decode = [&](TileCursor& c, int& m0, int& n0, int& b, int& split, int& bi, int& bo, int& kb_begin, int& nkb) {
+    if (c.z != c.zc) {  // batch / split decomposition: only when z changes
+      c.zc = c.z;
+      c.b = c.z / p.splits;
+      c.split = c.z - c.b * p.splits;
+      c.bo = c.b / epi.batch_inner;
+      c.bi = c.b - c.bo * epi.batch_inner;
+    }
+    b = c.b; split = c.split; bo = c.bo; bi = c.bi;
+    m0 = (c.mr * CL + cta_rank) * TC_BM;
+    n0 = c.nt * BN;
     kb_begin = split * p.kb_per_split;
     int kb_end = kb_begin + p.kb_per_split;
     if (kb_end > kblocks) kb_end = kblocks;
     nkb = kb_end - kb_begin;  // host guarantees >= 1
   };
+  TileCursor cur;
+  cur.init(unit_first, unit_stride, p.n_tiles, p.m_tiles / CL);
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t it = 0;  // running k-block counter across tiles
       int trace_tile = 0;
-      for (int t = unit_first; t < units; t += unit_stride, ++trace_tile) {
+      for (int t = unit_first; t < units; t += unit_stride, cur.next(), ++trace_tile) {
         int m0, n0, b, split, bi, bo, kb_begin, nkb;
-        decode(t, m0, n0, b, split, bi, bo, kb_begin, nkb);
+        decode(cur, m0, n0, b, split, bi, bo, kb_begin, nkb);
         for (int i = 0; i < nkb; ++i, ++it) {
           const int s = it % TC_STAGES;
           mbar_wait(empty_bar + s, ((it / TC_STAGES) & 1) ^ 1);
           if (i == 0) NPT_TRACE(p, 2 + trace_tile * 7 + 0);
           if (NPT_DBG(p, 4)) { mbar_arrive(full_bar + s); continue; }
-          mbar_expect_tx(full_bar + s, L::STAGE_BYTES);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           const int k0 = (kb_begin + i) * TC_BK;
+          if (CL > 1) {
+            // both CTAs of the pair load (own A rows, own half of B) and credit the LEADER's barrier
+            if (cta_rank == 0) mbar_expect_tx(full_bar + s, 2 * L::STAGE_BYTES);
+            if (A_MN) {
+              tma_load_4d_2sm(&tmA, full_bar + s, sa, m0, k0, bi, bo);
+              tma_load_4d_2sm(&tmA, full_bar + s, sa + 64 * TC_BK * 2, m0 + 64, k0, bi, bo);
+            } else {
+              tma_load_4d_2sm(&tmA, full_bar + s, sa, k0, m0, bi, bo);
+            }
+            const int nh = n0 + cta_rank * (BN / 2);  // this CTA's half of the tile's columns
+            if (B_MN) {
+#pragma unroll
+              for (int c = 0; c < BN / 128; ++c)
+                tma_load_4d_2sm(&tmB, full_bar + s, sb + c * 64 * TC_BK * 2, nh + c * 64, k0, bi, bo);
+            } else {
+              tma_load_4d_2sm(&tmB, full_bar + s, sb, k0, nh, bi, bo);
+            }
+            continue;
+          }
+          mbar_expect_tx(full_bar + s, L::STAGE_BYTES);
           if (A_MN) {
             tma_load_4d(&tmA, full_bar + s, sa, m0, k0, bi, bo);
             tma_load_4d(&tmA, full_bar + s, sa + 64 * TC_BK * 2, m0 + 64, k0, bi, bo);
           } else {
             tma_load_4d(&tmA, full_bar + s, sa, k0, m0, bi, bo);
           }
-          if (CL > 1) {
-            // this CTA fetches its half of the B tile and multicasts it to both CTAs of the pair
-            if (B_MN) {  // boxes {64 n, 32 k}: k rows [rank*32, rank*32+32) of every 64-wide n chunk
-#pragma unroll
-              for (int c = 0; c < BN / 64; ++c)
-                tma_load_4d_mc(&tmB, full_bar + s, sb + c * 64 * TC_BK * 2 + cta_rank * 32 * 128, n0 + c * 64,
-                               k0 + cta_rank * 32, bi, bo, (uint16_t)3);
-            } else {     // box {64 k, BN/2 n}: n rows [rank*BN/2, ...)
-              tma_load_4d_mc(&tmB, full_bar + s, sb + cta_rank * (BN / 2) * 128, k0, n0 + cta_rank * (BN / 2), bi, bo,
-                             (uint16_t)3);
-            }
-          } else if (B_MN) {
+          if (B_MN) {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
               tma_load_4d(&tmB, full_bar + s, sb + c * 64 * TC_BK * 2, n0 + c * 64, k0, bi, bo);
@@ -332,13 +404,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+    // ===== MMA issuer (CL = 2: the pair's leader only) =====
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc(TC_BM * CL, BN, A_MN, B_MN);
       uint32_t it = 0, tile_i = 0;
-      for (int t = unit_first; t < units; t += unit_stride, ++tile_i) {
+      for (int t = unit_first; t < units; t += unit_stride, cur.next(), ++tile_i) {
         int m0, n0, b, split, bi, bo, kb_begin, nkb;
-        decode(t, m0, n0, b, split, bi, bo, kb_begin, nkb);
+        decode(cur, m0, n0, b, split, bi, bo, kb_begin, nkb);
         const uint32_t acc = tile_i & 1;
         mbar_wait(tmem_empty_bar + acc, ((tile_i >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
@@ -357,12 +429,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           constexpr uint32_t adv_a = (A_MN ? 2048 : 32) >> 4, adv_b = (B_MN ? 2048 : 32) >> 4;
           if (!NPT_DBG(p, 2))
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            umma_bf16(d_tmem, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            if (CL > 1) umma_bf16_2sm(d_tmem, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc, (i > 0 || k > 0) ? 1u : 0u);
+            else        umma_bf16(d_tmem, da + (uint64_t)(k * adv_a), db + (uint64_t)(k * adv_b), idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
           // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
-          if (CL > 1) umma_commit_mc(empty_bar + s, (uint16_t)3); else umma_commit(empty_bar + s);
+          if (CL > 1) umma_commit_2sm(empty_bar + s, (uint16_t)3); else umma_commit(empty_bar + s);
         }
-        umma_commit(tmem_full_bar + acc);  // accumulator complete
+        if (CL > 1) umma_commit_2sm(tmem_full_bar + acc, (uint16_t)3); else umma_commit(tmem_full_bar + acc);  // accumulator complete
         NPT_TRACE(p, 2 + tile_i * 7 + 3);
       }
     }
@@ -395,9 +469,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t swz = (uint32_t)(lane & 7);
     const CUtensorMap* out_map = out_bf16 ? &tmCb : &tmC;
     uint32_t tile_i = 0, store_i = 0;  // store_i counts committed TMA-store groups (staging slot parity)
-    for (int t = unit_first; t < units; t += unit_stride, ++tile_i) {
+    for (int t = unit_first; t < units; t += unit_stride, cur.next(), ++tile_i) {
       int m0, n0, b, split, bi, bo, kb_begin, nkb;
-      decode(t, m0, n0, b, split, bi, bo, kb_begin, nkb);
+      decode(cur, m0, n0, b, split, bi, bo, kb_begin, nkb);
       const uint32_t acc = tile_i & 1;
       const int mrow0 = m0 + quarter * 32;  // first row of this warp's 32-row band
       const int m = mrow0 + lane;
@@ -428,7 +502,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       auto release_acc = [&]() {  // this warp has read everything it needs from the accumulator
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+        if (lane == 0) {
+          if (CL > 1) mbar_arrive_cluster(tmem_empty_bar + acc, 0); else mbar_arrive(tmem_empty_bar + acc);
+        }
         if (warp == 2 && lane == 0) NPT_TRACE(p, 2 + tile_i * 7 + 5);
       };
       // one 32-column chunk: epilogue math on this lane's row, then staging (+ TMA store)
@@ -538,9 +614,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool want_bf16 = !p.raw && epi.Cb != nullptr;
     const bool masked = !p.raw && epi.mask != nullptr;
     uint32_t tile_i = 0, store_i = 0;  // store_i counts committed TMA-store groups (staging buffer parity)
-    for (int t = unit_first; t < units; t += unit_stride, ++tile_i) {
+    for (int t = unit_first; t < units; t += unit_stride, cur.next(), ++tile_i) {
       int m0, n0, b, split, bi, bo, kb_begin, nkb;
-      decode(t, m0, n0, b, split, bi, bo, kb_begin, nkb);
+      decode(cur, m0, n0, b, split, bi, bo, kb_begin, nkb);
       const uint32_t acc = tile_i & 1;
       const int mrow0 = m0 + quarter * 32;  // first row of this warp's 32-row band
       const int m = mrow0 + lane;
@@ -731,10 +807,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync();  // no CTA leaves while its peer can still multicast into it
+  if (CL > 1) cluster_sync();  // no CTA leaves while its peer can still signal it / read its shared memory
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<L::TMEM_COLS>(tmem_base);
+    tmem_dealloc<L::TMEM_COLS, CL>(tmem_base);
   }
 }
 
@@ -742,7 +818,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, bool A_MN, bool B_MN, int CL, int EPI>
 static int launch_tc_cl(const TcParams& p, const GemmEpilogue& epi, float* partial, const CUtensorMap& tmA,
                         const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCb, cudaStream_t st) {
-  using L = TcSmem<BN>;
+  using L = TcSmem<BN, CL>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL, EPI>;
   constexpr int threads = EPI == EPI_GENERAL ? TC_THREADS : TC_THREADS_FAST;
   static bool attr_set = false;
@@ -792,8 +868,16 @@ template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const TcParams& p, const GemmEpilogue& epi, float* partial, const CUtensorMap& tmA,
                      const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCb, int cl, int kind,
                      cudaStream_t st) {
-  if (cl == 2) return launch_tc_cl<BN, A_MN, B_MN, 2, EPI_GENERAL>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
   if (kind == EPI_GENERAL) return launch_tc_cl<BN, A_MN, B_MN, 1, EPI_GENERAL>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
+  if constexpr (BN >= 128 && !(BN == 192 && B_MN)) {  // CTA pairs (cta_group::2)
+    if (cl == 2) {
+#define NPT_X(K) if (kind == (K)) return launch_tc_cl<BN, A_MN, B_MN, 2, (K)>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
+      NPT_TC_FAST_KINDS(NPT_X)
+#undef NPT_X
+      return launch_tc_cl<BN, A_MN, B_MN, 2, EPI_DYNAMIC>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
+    }
+  }
+  NPT_REQUIRE(cl == 1, "gemm(tc): no CTA-pair kernel for this tile shape");
 #define NPT_X(K) if (kind == (K)) return launch_tc_cl<BN, A_MN, B_MN, 1, (K)>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
   NPT_TC_FAST_KINDS(NPT_X)
 #undef NPT_X

@@ -144,20 +144,30 @@ def test_gemm_bf16_persistent_many_tiles_and_fused_epilogues():
 
 @pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
 @pytest.mark.parametrize("M,N,K", [(16384, 384, 200), (9984, 1152, 136), (16384, 1536, 72), (20480, 128, 320)])
-def test_gemm_bf16_cta_pairs_multicast(M, N, K, ta, tb, monkeypatch):
-    """Shapes large enough for the 2-CTA cluster path (B tile fetched half by each CTA and TMA-multicast
-    to both), all four operand layouts, BN = 128 / 192 / 256, ragged K tails.  The path is opt-in
-    (NUMPITRON_GEMM_CLUSTER=1, read at every launch)."""
-    monkeypatch.setenv("NUMPITRON_GEMM_CLUSTER", "1")
+def test_gemm_bf16_cta_pairs(M, N, K, ta, tb, monkeypatch):
+    """Shapes large enough for the CTA-pair kernels (tcgen05 cta_group::2: one 256 x BN MMA per pair, each
+    CTA staging its own A rows and half of the B tile), all four operand layouts, BN = 128 / 192 / 256,
+    ragged K tails, fp32 and bf16 outputs, bias.  The pair kernels must reproduce the single-CTA ones
+    bit for bit (NUMPITRON_GEMM_PAIR=0, read at every launch)."""
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     a = torch.randn((K, M) if ta else (M, K), device="cuda", generator=g).bfloat16()
     b = torch.randn((N, K) if tb else (K, N), device="cuda", generator=g).bfloat16()
-    c = rt.empty((M, N))
-    ops.gemm(a, b, M, N, K, lda=a.shape[1], ldb=b.shape[1], trans_a=ta, trans_b=tb, C_out=c, ldc=N, mode=1)
+    bias = torch.randn(N, device="cuda", generator=g)
     ref = (a.double().T if ta else a.double()) @ (b.double().T if tb else b.double())
-    torch.cuda.synchronize()
-    err = (c.double() - ref).abs().max().item() / ref.abs().max().item()
+    out = {}
+    for pair in ("1", "0"):
+        monkeypatch.setenv("NUMPITRON_GEMM_PAIR", pair)
+        c = rt.empty((M, N))
+        cb = rt.empty((M, N), torch.bfloat16)
+        ops.gemm(a, b, M, N, K, lda=a.shape[1], ldb=b.shape[1], trans_a=ta, trans_b=tb, C_out=c, ldc=N, mode=1)
+        ops.gemm(a, b, M, N, K, lda=a.shape[1], ldb=b.shape[1], trans_a=ta, trans_b=tb, Cb_out=cb, ldcb=N, bias=bias, mode=1)
+        torch.cuda.synchronize()
+        out[pair] = (host(c), host(cb))
+    err = np.abs(out["1"][0] - host(ref)).max() / ref.abs().max().item()
     assert err < 1e-5, err
+    np.testing.assert_array_equal(out["1"][0], out["0"][0])
+    np.testing.assert_array_equal(out["1"][1], out["0"][1])
+    np.testing.assert_array_equal(out["1"][1], bf16_round(out["1"][0] + host(bias)[None, :]))
 
 
 @pytest.mark.parametrize("M,K,N", [(16384, 384, 1536), (300, 136, 200), (128, 64, 72)])
