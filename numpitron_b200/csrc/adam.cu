@@ -29,6 +29,8 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 
 __global__ void __launch_bounds__(kAdamThreads)
 adam_multi_kernel(const npt_adam_tensor* __restrict__ tensors, int n_tensors, AdamScalars s) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   // locate this block's tensor and chunk (n_tensors is small: a linear walk is fine)
   int64_t chunk = blockIdx.x;
   int ti = 0;
@@ -102,7 +104,7 @@ int npt_adam_step(const npt_adam_tensor* tensors_dev, const npt_adam_tensor* ten
   }
   if (blocks == 0) return 0;
   AdamScalars s{lr, b1, omb1, b2, omb2, c1, c2, eps};
-  adam_multi_kernel<<<(unsigned)blocks, kAdamThreads, 0, (cudaStream_t)stream>>>(tensors_dev, n_tensors, s);
+  NPT_CHECK_CUDA(launch_pdl(adam_multi_kernel, dim3((unsigned)blocks), dim3(kAdamThreads), 0, (cudaStream_t)stream, tensors_dev, n_tensors, s));
   NPT_LAUNCH_CHECK();
   return 0;
 }

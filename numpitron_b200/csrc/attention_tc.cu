@@ -124,6 +124,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();     // set-up above is private; global memory is touched only from here on
+  pdl_trigger();  // persistent grid: the next kernel may be scheduled behind this one
   // TMEM columns: S[2] at 0 / 128, O[2] at 256 / 320
 
   if (warp == 0) {
@@ -296,6 +298,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                      float* __restrict__ D, int64_t rows /* B*S*h */, int S, int h) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const int part = threadIdx.x & 7;
   float acc = 0.f;
@@ -421,6 +425,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();     // set-up above is private; global memory is touched only from here on
+  pdl_trigger();  // persistent grid: the next kernel may be scheduled behind this one
   const uint32_t tmem_S = tmem, tmem_dP = tmem + 128, tmem_dK = tmem + 256, tmem_dV = tmem + 320;
 
   if (warp == 0) {
@@ -575,6 +581,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();     // set-up above is private; global memory is touched only from here on
+  pdl_trigger();  // persistent grid: the next kernel may be scheduled behind this one
   const uint32_t tmem_S = tmem, tmem_dP = tmem + 128, tmem_dQ = tmem + 256;
 
   if (warp == 0) {
@@ -713,8 +721,8 @@ int npt_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int32_t 
     attr = true;
   }
   const int grid = persistent_grid(B * h * (S / 128));
-  attn_fwd_kernel<<<grid, AT_THREADS, AttnFwdSmem::TOTAL, (cudaStream_t)stream>>>(
-      tm, (__nv_bfloat16*)out_bf16, lse, B, S, h, 1.0f / divisor);
+  NPT_CHECK_CUDA(launch_pdl(attn_fwd_kernel, dim3(grid), dim3(AT_THREADS), AttnFwdSmem::TOTAL, (cudaStream_t)stream, tm,
+                            (__nv_bfloat16*)out_bf16, lse, B, S, h, 1.0f / divisor));
   NPT_LAUNCH_CHECK();
   return 0;
 }
@@ -731,8 +739,8 @@ int npt_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_
   cudaStream_t st = (cudaStream_t)stream;
   float* D = (float*)workspace;
   const int64_t rows = (int64_t)B * S * h;
-  attn_bwd_prep_kernel<<<(unsigned)cdiv(rows * 8, 256), 256, 0, st>>>((const __nv_bfloat16*)out_bf16,
-                                                                      (const __nv_bfloat16*)d_out_bf16, D, rows, S, h);
+  NPT_CHECK_CUDA(launch_pdl(attn_bwd_prep_kernel, dim3((unsigned)cdiv(rows * 8, 256)), dim3(256), 0, st,
+                            (const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)d_out_bf16, D, rows, S, h));
   NPT_LAUNCH_CHECK();
   CUtensorMap tmQKV, tmDO;
   if (int rc = make_map_bf16_2d(&tmQKV, qkv_bf16, (int64_t)h * 3 * Dh, (int64_t)B * S, (int64_t)h * 3 * Dh, 64, 128)) return rc;
@@ -745,9 +753,11 @@ int npt_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_
   }
   const int grid = persistent_grid(B * h * (S / 128));
   const float inv_div = 1.0f / divisor;
-  attn_bwd_dkv_kernel<<<grid, AT_THREADS, AttnDkvSmem::TOTAL, st>>>(tmQKV, tmDO, lse, D, (__nv_bfloat16*)dqkv_bf16, B, S, h, inv_div);
+  NPT_CHECK_CUDA(launch_pdl(attn_bwd_dkv_kernel, dim3(grid), dim3(AT_THREADS), AttnDkvSmem::TOTAL, st, tmQKV, tmDO, lse, D,
+                            (__nv_bfloat16*)dqkv_bf16, B, S, h, inv_div));
   NPT_LAUNCH_CHECK();
-  attn_bwd_dq_kernel<<<grid, AT_THREADS, AttnDqSmem::TOTAL, st>>>(tmQKV, tmDO, lse, D, (__nv_bfloat16*)dqkv_bf16, B, S, h, inv_div);
+  NPT_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel, dim3(grid), dim3(AT_THREADS), AttnDqSmem::TOTAL, st, tmQKV, tmDO, lse, D,
+                            (__nv_bfloat16*)dqkv_bf16, B, S, h, inv_div));
   NPT_LAUNCH_CHECK();
   return 0;
 }

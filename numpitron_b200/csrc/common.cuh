@@ -1,5 +1,6 @@
 // Shared helpers for the numpitron_b200 kernels (sm_100a only).
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -41,6 +42,34 @@ constexpr unsigned kFull = 0xffffffffu;
 
 int sm_count();
 int sm_margin();  // SMs persistent GEMMs leave free while a collective overlaps them
+
+// ---- programmatic dependent launch ----------------------------------------------------------------
+// The training step is ~200 short kernels in one stream / CUDA graph; each pays its launch latency
+// and prologue after the previous kernel has drained.  Kernels launched through launch_pdl() may be
+// scheduled while their predecessor is still running: they do their private set-up (barrier init,
+// TMEM allocation, index math), then pdl_wait() blocks until EVERY prerequisite grid has completed
+// and its writes are visible — nothing before pdl_wait() may read or write global memory.
+// pdl_trigger() tells the scheduler this CTA no longer minds the dependent grid being launched (the
+// dependent starts once all CTAs have triggered or exited).  NUMPITRON_PDL=0 disables the attribute;
+// the device-side calls are then no-ops.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -18,6 +18,8 @@ static unsigned stream_grid(int64_t nvec) {
 __global__ void __launch_bounds__(kEwThreads)
 relu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
                 int64_t n, bool vec) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   if (vec) {
     const int64_t nv = n >> 2;
@@ -44,6 +46,8 @@ relu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat1
 __global__ void __launch_bounds__(kEwThreads)
 relu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
                 __nv_bfloat16* __restrict__ dxb, int64_t n, bool vec) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   if (vec) {
     const int64_t nv = n >> 2;
@@ -73,6 +77,8 @@ relu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float
 __global__ void __launch_bounds__(kEwThreads)
 cast_bf16_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst,
                  int64_t ld_dst, int64_t rows, int64_t cols, bool vec) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   if (vec) {  // contiguous on both sides, multiple of 4, aligned
     const int64_t nv = (rows * cols) >> 2;
@@ -92,6 +98,8 @@ cast_bf16_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* _
 __global__ void __launch_bounds__(256)
 colsum_stage1_kernel(const void* __restrict__ xv, int x_is_bf16, int64_t ld, float* __restrict__ partial,
                      int64_t rows, int cols, int64_t rows_per_block) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   const float* x = reinterpret_cast<const float*>(xv);
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xv);
   __shared__ float sm[8][33];
@@ -118,6 +126,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(256)
 colsum_stage1_vec_kernel(const void* __restrict__ xv, int64_t ld, float* __restrict__ partial, int64_t rows,
                          int cols, int64_t rows_per_block) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   __shared__ float4 sm[8][32];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + cx) * 4;
@@ -159,6 +169,8 @@ colsum_stage1_vec_kernel(const void* __restrict__ xv, int64_t ld, float* __restr
 // Stage 2: 32 columns x 32 row-lanes per block (independent loads), fixed-order smem tree.
 __global__ void __launch_bounds__(1024)
 colsum_stage2_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int cols) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -188,6 +200,8 @@ static int colsum_parts(int64_t rows, int cols) {
 // mean of n floats: single block, fixed-order tree -> deterministic.
 __global__ void __launch_bounds__(1024)
 mean_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   __shared__ float red[32];
   float s = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
@@ -204,8 +218,8 @@ extern "C" {
 int npt_relu_fwd(const float* x, float* y, void* y_bf16, int64_t n, void* stream) {
   if (n <= 0) return 0;
   const bool vec = aligned16(x) && aligned16(y) && (!y_bf16 || aligned8(y_bf16));
-  relu_fwd_kernel<<<stream_grid(n / 4 + 1), kEwThreads, 0, (cudaStream_t)stream>>>(
-      x, y, (__nv_bfloat16*)y_bf16, n, vec);
+  NPT_CHECK_CUDA(launch_pdl(relu_fwd_kernel, dim3(stream_grid(n / 4 + 1)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
+      x, y, (__nv_bfloat16*)y_bf16, n, vec));
   NPT_LAUNCH_CHECK();
   return 0;
 }
@@ -213,8 +227,8 @@ int npt_relu_fwd(const float* x, float* y, void* y_bf16, int64_t n, void* stream
 int npt_relu_bwd(const float* x, const float* dy, float* dx, void* dx_bf16, int64_t n, void* stream) {
   if (n <= 0) return 0;
   const bool vec = aligned16(x) && aligned16(dy) && aligned16(dx) && (!dx_bf16 || aligned8(dx_bf16));
-  relu_bwd_kernel<<<stream_grid(n / 4 + 1), kEwThreads, 0, (cudaStream_t)stream>>>(
-      x, dy, dx, (__nv_bfloat16*)dx_bf16, n, vec);
+  NPT_CHECK_CUDA(launch_pdl(relu_bwd_kernel, dim3(stream_grid(n / 4 + 1)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
+      x, dy, dx, (__nv_bfloat16*)dx_bf16, n, vec));
   NPT_LAUNCH_CHECK();
   return 0;
 }
@@ -225,8 +239,8 @@ int npt_cast_f32_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_ds
   if (rows <= 0 || cols <= 0) return 0;
   const bool vec = ld_src == cols && ld_dst == cols && ((rows * cols) % 4 == 0) && aligned16(src) && aligned8(dst);
   const int64_t work = vec ? (rows * cols) / 4 : rows * ld_dst;
-  cast_bf16_kernel<<<stream_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(
-      src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols, vec);
+  NPT_CHECK_CUDA(launch_pdl(cast_bf16_kernel, dim3(stream_grid(work)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
+      src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols, vec));
   NPT_LAUNCH_CHECK();
   return 0;
 }
@@ -246,21 +260,21 @@ int npt_colsum(const void* x, int32_t x_is_bf16, int64_t ld, float* out, int64_t
   const bool vec = cols % 4 == 0 && ld % 4 == 0 && aligned16(workspace) && (x_is_bf16 ? aligned8(x) : aligned16(x));
   if (vec) {
     dim3 grid((unsigned)cdiv(cols, 128), (unsigned)parts);
-    if (x_is_bf16) colsum_stage1_vec_kernel<true><<<grid, 256, 0, st>>>(x, ld, (float*)workspace, rows, cols, rpb);
-    else colsum_stage1_vec_kernel<false><<<grid, 256, 0, st>>>(x, ld, (float*)workspace, rows, cols, rpb);
+    if (x_is_bf16) NPT_CHECK_CUDA(launch_pdl(colsum_stage1_vec_kernel<true>, dim3(grid), dim3(256), 0, st, x, ld, (float*)workspace, rows, cols, rpb));
+    else NPT_CHECK_CUDA(launch_pdl(colsum_stage1_vec_kernel<false>, dim3(grid), dim3(256), 0, st, x, ld, (float*)workspace, rows, cols, rpb));
   } else {
     dim3 grid((unsigned)cdiv(cols, 32), (unsigned)parts);
-    colsum_stage1_kernel<<<grid, 256, 0, st>>>(x, x_is_bf16, ld, (float*)workspace, rows, cols, rpb);
+    NPT_CHECK_CUDA(launch_pdl(colsum_stage1_kernel, dim3(grid), dim3(256), 0, st, x, x_is_bf16, ld, (float*)workspace, rows, cols, rpb));
   }
   NPT_LAUNCH_CHECK();
-  colsum_stage2_kernel<<<(unsigned)cdiv(cols, 32), 1024, 0, st>>>((const float*)workspace, out, parts, cols);
+  NPT_CHECK_CUDA(launch_pdl(colsum_stage2_kernel, dim3((unsigned)cdiv(cols, 32)), dim3(1024), 0, st, (const float*)workspace, out, parts, cols));
   NPT_LAUNCH_CHECK();
   return 0;
 }
 
 int npt_mean(const float* x, float* out, int64_t n, void* stream) {
   NPT_REQUIRE(n > 0, "mean: n must be positive");
-  mean_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, out, n);
+  NPT_CHECK_CUDA(launch_pdl(mean_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, x, out, n));
   NPT_LAUNCH_CHECK();
   return 0;
 }

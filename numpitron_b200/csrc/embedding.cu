@@ -23,6 +23,8 @@ embedding_gather_kernel(const uint16_t* __restrict__ tokens, const float* __rest
                         const float* __restrict__ pos, float* __restrict__ out,
                         __nv_bfloat16* __restrict__ outb, int64_t T, int S, int d, int chunk_start,
                         int chunk_end, int masked) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
@@ -42,6 +44,8 @@ embedding_gather_kernel(const uint16_t* __restrict__ tokens, const float* __rest
 __global__ void __launch_bounds__(256)
 add_pos_kernel(const float* x, const float* __restrict__ pos, float* out, __nv_bfloat16* __restrict__ xb,
                int64_t T, int S, int d) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   const int64_t n = T * d;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t t = i / d;
@@ -64,6 +68,8 @@ __device__ __forceinline__ int local_id(int tok, int chunk_start, int chunk_end)
 __global__ void __launch_bounds__(kSaChunk)
 sa_chunk_kernel(const uint16_t* __restrict__ tokens, int* __restrict__ table, int* __restrict__ rank,
                 int64_t T, int V, int chunk_start, int chunk_end) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   __shared__ int ids[kSaChunk];
   const int64_t t = (int64_t)blockIdx.x * kSaChunk + threadIdx.x;
   const int v = (t < T) ? local_id(tokens[t], chunk_start, chunk_end) : -1;
@@ -79,6 +85,8 @@ sa_chunk_kernel(const uint16_t* __restrict__ tokens, int* __restrict__ table, in
 // Column scan over chunks, in place: table[c][v] <- sum_{c' < c} table[c'][v]; counts[v] <- total.
 __global__ void __launch_bounds__(256)
 sa_colscan_kernel(int* __restrict__ table, int* __restrict__ counts, int nchunks, int V) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
   int run = 0;
@@ -93,6 +101,8 @@ sa_colscan_kernel(int* __restrict__ table, int* __restrict__ counts, int nchunks
 // Single block exclusive scan of counts[0..V) into offsets[0..V].
 __global__ void __launch_bounds__(1024)
 sa_scan_kernel(const int* __restrict__ counts, int* __restrict__ offsets, int V) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   __shared__ int part[1024];
   const int per = (V + 1023) / 1024;
   const int lo = threadIdx.x * per;
@@ -120,6 +130,8 @@ __global__ void __launch_bounds__(256)
 sa_fill_kernel(const uint16_t* __restrict__ tokens, const int* __restrict__ table, const int* __restrict__ rank,
                const int* __restrict__ offsets, int* __restrict__ order, int64_t T, int V, int chunk_start,
                int chunk_end) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const int v = local_id(tokens[t], chunk_start, chunk_end);
@@ -132,6 +144,8 @@ sa_fill_kernel(const uint16_t* __restrict__ tokens, const int* __restrict__ tabl
 __global__ void __launch_bounds__(128)
 sa_accumulate_kernel(const int* __restrict__ offsets, const int* __restrict__ order,
                      const float* __restrict__ d_out, float* __restrict__ grad, int64_t ldG, int d) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   const int v = blockIdx.x;
   const int beg = offsets[v], end = offsets[v + 1];
   const int c = blockIdx.y * 128 + threadIdx.x;
@@ -179,8 +193,8 @@ int npt_embedding_gather(const uint16_t* tokens, const float* E, int64_t ldE, co
   NPT_REQUIRE(T >= 0 && S > 0 && d > 0 && chunk_end >= chunk_start, "embedding_gather: bad shape");
   if (T == 0) return 0;
   const int warps = 8;
-  embedding_gather_kernel<<<(unsigned)cdiv(T, warps), warps * 32, 0, (cudaStream_t)stream>>>(
-      tokens, E, ldE, pos, out, (__nv_bfloat16*)out_bf16, T, S, d, chunk_start, chunk_end, masked);
+  NPT_CHECK_CUDA(launch_pdl(embedding_gather_kernel, dim3((unsigned)cdiv(T, warps)), dim3(warps * 32), 0, (cudaStream_t)stream, 
+      tokens, E, ldE, pos, out, (__nv_bfloat16*)out_bf16, T, S, d, chunk_start, chunk_end, masked));
   NPT_LAUNCH_CHECK();
   return 0;
 }
@@ -190,7 +204,7 @@ int npt_add_pos(const float* x, const float* pos, float* out, void* x_bf16, int6
   int64_t blocks = cdiv(T * d, 256);
   int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  add_pos_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, pos, out, (__nv_bfloat16*)x_bf16, T, S, d);
+  NPT_CHECK_CUDA(launch_pdl(add_pos_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, pos, out, (__nv_bfloat16*)x_bf16, T, S, d));
   NPT_LAUNCH_CHECK();
   return 0;
 }
@@ -218,16 +232,16 @@ int npt_embedding_scatter_add(const uint16_t* tokens, const float* d_out, float*
   int* order = (int*)(ws + L.order);
   const int nchunks = (int)cdiv(T, kSaChunk);
   NPT_CHECK_CUDA(cudaMemsetAsync(table, 0, (size_t)nchunks * V_local * 4, st));
-  sa_chunk_kernel<<<nchunks, kSaChunk, 0, st>>>(tokens, table, rank, T, V_local, chunk_start, chunk_end);
+  NPT_CHECK_CUDA(launch_pdl(sa_chunk_kernel, dim3(nchunks), dim3(kSaChunk), 0, st, tokens, table, rank, T, V_local, chunk_start, chunk_end));
   NPT_LAUNCH_CHECK();
-  sa_colscan_kernel<<<(unsigned)cdiv(V_local, 256), 256, 0, st>>>(table, counts, nchunks, V_local);
+  NPT_CHECK_CUDA(launch_pdl(sa_colscan_kernel, dim3((unsigned)cdiv(V_local, 256)), dim3(256), 0, st, table, counts, nchunks, V_local));
   NPT_LAUNCH_CHECK();
-  sa_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, V_local);
+  NPT_CHECK_CUDA(launch_pdl(sa_scan_kernel, dim3(1), dim3(1024), 0, st, counts, offsets, V_local));
   NPT_LAUNCH_CHECK();
-  sa_fill_kernel<<<(unsigned)cdiv(T, 256), 256, 0, st>>>(tokens, table, rank, offsets, order, T, V_local, chunk_start, chunk_end);
+  NPT_CHECK_CUDA(launch_pdl(sa_fill_kernel, dim3((unsigned)cdiv(T, 256)), dim3(256), 0, st, tokens, table, rank, offsets, order, T, V_local, chunk_start, chunk_end));
   NPT_LAUNCH_CHECK();
   dim3 grid((unsigned)V_local, (unsigned)cdiv(d, 128));
-  sa_accumulate_kernel<<<grid, 128, 0, st>>>(offsets, order, d_out, grad, ldG, d);
+  NPT_CHECK_CUDA(launch_pdl(sa_accumulate_kernel, dim3(grid), dim3(128), 0, st, offsets, order, d_out, grad, ldG, d));
   NPT_LAUNCH_CHECK();
   return 0;
 }

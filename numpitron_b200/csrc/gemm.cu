@@ -31,6 +31,8 @@ GemmEpilogue make_epilogue(const npt_gemm_args& a) {
 // partial layout: [split][batch][M][N] fp32, contiguous.
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, GemmEpilogue e, int splits, int batch) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   const int64_t mn = (int64_t)e.M * e.N;
   const int64_t total4 = ((int64_t)batch * mn + 3) / 4;
   const bool n4 = (e.N % 4) == 0;
@@ -118,7 +120,7 @@ int npt_gemm(const npt_gemm_args* args, void* stream) {
     int64_t blocks = cdiv(total4, 256);
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(partial, epi, splits, a.batch);
+    NPT_CHECK_CUDA(launch_pdl(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, st, partial, epi, splits, a.batch));
     NPT_LAUNCH_CHECK();
   }
   return 0;

@@ -88,6 +88,12 @@ static int tc_bn(const npt_gemm_args& a) {
   return best;
 }
 
+// Split-K factor for launches with too few tiles to fill the GPU (the weight-gradient GEMMs: a few
+// hundred rows and columns, K = all the tokens).  Picks the split count with the shortest modelled
+// makespan: waves x (k-blocks per unit + the unit's fixed cost) + the reduce pass over the partials.
+// What matters most is the wave count: 18 tiles x 9 splits = 162 units is TWO waves on 148 SMs,
+// 18 x 8 = 144 is one (the first version rounded the split count up and ran two waves on three of
+// the four weight gradients of a transformer block).
 int gemm_tc_splits(const npt_gemm_args& a) {
   if (a.relu_bits_out || a.mask_bits) return 1;  // the packed-mask epilogue runs in the GEMM kernel itself
   const int bn = tc_bn(a);
@@ -95,12 +101,20 @@ int gemm_tc_splits(const npt_gemm_args& a) {
   const int64_t kblocks = cdiv(a.K, TC_BK);
   const int64_t target = (int64_t)sm_count();
   if (tiles * 2 > target || kblocks < 8) return 1;
-  int64_t s = (target + tiles - 1) / tiles;
-  if (s > kblocks / 4) s = kblocks / 4;  // >= 4 k-blocks (256 k) per split
-  if (s > 64) s = 64;
-  if (s < 1) s = 1;
-  const int64_t kps = cdiv(kblocks, s);
-  return (int)cdiv(kblocks, kps);  // no empty split
+  const double kblock_us = 0.0014 * (128 + bn);                       // shared-memory fill at ~64 B/clk
+  const double unit_us = 1.5;                                          // accumulator drain + partial store
+  const double reduce_us = (double)a.M * a.N * a.batch * 4.0 / 3.0e6;  // per split: partials re-read at ~3 TB/s
+  int64_t best = 1;
+  double best_cost = 0.0;
+  for (int64_t s = 1; s <= 64 && s <= kblocks / 4; ++s) {               // >= 4 k-blocks (256 k) per split
+    const int64_t kps = cdiv(kblocks, s);
+    const int64_t s_eff = cdiv(kblocks, kps);                          // no empty split
+    if (s_eff != s) continue;
+    const int64_t waves = cdiv(tiles * s, target);
+    const double cost = (double)waves * ((double)kps * kblock_us + unit_us) + (s > 1 ? 3.0 + (double)s * reduce_us : 0.0);
+    if (s == 1 || cost < best_cost) { best = s; best_cost = cost; }
+  }
+  return (int)best;
 }
 
 // Can this launch use the fast epilogue (gemm_tc_kernel.cuh)?  One output kind, written by TMA, no

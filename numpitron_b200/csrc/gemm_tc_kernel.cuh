@@ -323,6 +323,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CL > 1) cluster_sync();  // the peer's barriers are initialised before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above is private set-up; from here on global memory is read and written, so the
+  // preceding kernels must have completed.  The grid is persistent (no CTA waits to be scheduled),
+  // so the next kernel may be launched right away and do its own set-up behind this one.
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x == 0) NPT_TRACE(p, 1);
   const int cta_rank = CL > 1 ? (int)cluster_ctarank() : 0;
   // work units: one tile (CL = 1) or one vertical pair of tiles (CL = 2) per step of the persistent loop
@@ -830,7 +835,7 @@ static int launch_tc_cl(const TcParams& p, const GemmEpilogue& epi, float* parti
   if (grid < 1) grid = 1;
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (CL == 1) {
-    kern<<<grid, threads, L::TOTAL, st>>>(tmA, tmB, tmC, tmCb, p, epi, partial);
+    NPT_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(threads), L::TOTAL, st, tmA, tmB, tmC, tmCb, p, epi, partial));
   } else {
     grid -= grid % CL;
     cudaLaunchConfig_t cfg = {};
@@ -838,13 +843,15 @@ static int launch_tc_cl(const TcParams& p, const GemmEpilogue& epi, float* parti
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     NPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmCb, p, epi, partial));
   }
   NPT_LAUNCH_CHECK();

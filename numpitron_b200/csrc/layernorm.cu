@@ -19,6 +19,8 @@ ln_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                    float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
                    float* __restrict__ mean_out, float* __restrict__ var_out,
                    int64_t rows, int d, float eps) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.x * kLnWarps + warp;
   if (row >= rows) return;
@@ -84,6 +86,8 @@ ln_fwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma
                     float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
                     float* __restrict__ mean_out, float* __restrict__ var_out,
                     int64_t rows, int d, float eps) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
   const float* xr = x + row * d;
@@ -118,6 +122,8 @@ ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ dy, float* __restrict__ dx,
                    __nv_bfloat16* __restrict__ dxb, float* __restrict__ partial,
                    int64_t rows, int d, float eps) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   extern __shared__ float sm[];  // [kLnWarps][2][d]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = d >> 2;
@@ -221,6 +227,8 @@ ln_bwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma
                     const float* __restrict__ dy, float* __restrict__ dx,
                     __nv_bfloat16* __restrict__ dxb, float* __restrict__ partial,
                     int64_t rows, int d, float eps) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   __shared__ float red[32];
   // per-thread column accumulators live in `partial` directly (each block owns its slice,
   // each column is touched by exactly one thread of the block -> no race).
@@ -258,6 +266,8 @@ ln_bwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma
 __global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out0,
                        float* __restrict__ out1, int nblocks, int d) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -285,8 +295,8 @@ static int launch_fwd(const float* x, const float* g, const float* b, const floa
                       void* yb, float* mean, float* var, int64_t rows, int d, float eps,
                       cudaStream_t st) {
   const int64_t grid = cdiv(rows, kLnWarps);
-  ln_fwd_warp_kernel<NV><<<(unsigned)grid, kLnWarps * 32, 0, st>>>(
-      x, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps);
+  NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st, 
+      x, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
   NPT_LAUNCH_CHECK();
   return 0;
 }
@@ -298,8 +308,8 @@ static int launch_bwd(const float* x, const float* g, const float* mean, const f
   const size_t smem = (size_t)kLnWarps * 2 * d * sizeof(float);
   NPT_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_warp_kernel<NV>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ln_bwd_warp_kernel<NV><<<nblocks, kLnWarps * 32, smem, st>>>(
-      x, g, mean, var, dy, dx, (__nv_bfloat16*)dxb, partial, rows, d, eps);
+  NPT_CHECK_CUDA(launch_pdl(ln_bwd_warp_kernel<NV>, dim3(nblocks), dim3(kLnWarps * 32), smem, st, 
+      x, g, mean, var, dy, dx, (__nv_bfloat16*)dxb, partial, rows, d, eps));
   NPT_LAUNCH_CHECK();
   return 0;
 }
@@ -330,8 +340,8 @@ int npt_layernorm_fwd(const float* x, const float* gamma, const float* beta, con
       default: return launch_fwd<8>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
     }
   }
-  ln_fwd_block_kernel<<<(unsigned)rows, 256, 0, st>>>(x, gamma, beta, residual, y,
-                                                      (__nv_bfloat16*)y_bf16, mean, var, rows, d, eps);
+  NPT_CHECK_CUDA(launch_pdl(ln_fwd_block_kernel, dim3((unsigned)rows), dim3(256), 0, st, x, gamma, beta, residual, y,
+                                                      (__nv_bfloat16*)y_bf16, mean, var, rows, d, eps));
   NPT_LAUNCH_CHECK();
   return 0;
 }
@@ -373,11 +383,11 @@ int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, con
   } else {
     int64_t cap = (int64_t)sm_count() * 2;
     nblocks = (int)(rows < cap ? rows : cap);
-    ln_bwd_block_kernel<<<nblocks, 256, 0, st>>>(x, gamma, mean, var, dy, dx,
-                                                  (__nv_bfloat16*)dx_bf16, partial, rows, d, eps);
+    NPT_CHECK_CUDA(launch_pdl(ln_bwd_block_kernel, dim3(nblocks), dim3(256), 0, st, x, gamma, mean, var, dy, dx,
+                                                  (__nv_bfloat16*)dx_bf16, partial, rows, d, eps));
     NPT_LAUNCH_CHECK();
   }
-  reduce_partials_kernel<<<(unsigned)cdiv(2 * (int64_t)d, 32), 1024, 0, st>>>(partial, dgamma, dbeta, nblocks, d);
+  NPT_CHECK_CUDA(launch_pdl(reduce_partials_kernel, dim3((unsigned)cdiv(2 * (int64_t)d, 32)), dim3(1024), 0, st, partial, dgamma, dbeta, nblocks, d));
   NPT_LAUNCH_CHECK();
   return 0;
 }

@@ -1,4 +1,5 @@
 // Library plumbing: error text, version, device query.
+#include <stdlib.h>
 #include <stdarg.h>
 
 #include "common.cuh"
@@ -32,6 +33,15 @@ int sm_count() {
 
 static int g_sm_margin = 0;
 int sm_margin() { return g_sm_margin; }
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("NUMPITRON_PDL");
+    cached = (e && e[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
 
 }  // namespace npt
 

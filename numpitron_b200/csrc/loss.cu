@@ -27,6 +27,8 @@ ce_kernel(const float* __restrict__ logits, int64_t ld, const uint16_t* __restri
           float* __restrict__ loss, float* __restrict__ grad, int64_t ldg,
           __nv_bfloat16* __restrict__ gradb, int64_t ldgb, int64_t T, int V, int chunk_start,
           int chunk_end) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
+  pdl_trigger();
   __shared__ float red[32];
   Group<BLOCK> g{red};
   const int64_t row = BLOCK ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -93,11 +95,11 @@ static int launch_ce(const float* logits, int64_t ld, const uint16_t* labels, fl
                      void* gradb, int64_t ldgb, int64_t T, int V, int cs, int ce, cudaStream_t st) {
   if (V <= 2048) {
     const int warps = 8;
-    ce_kernel<false, STAGE><<<(unsigned)cdiv(T, warps), warps * 32, 0, st>>>(
-        logits, ld, labels, rowmax, picked, sumexp, loss, grad, ldg, (__nv_bfloat16*)gradb, ldgb, T, V, cs, ce);
+    NPT_CHECK_CUDA(launch_pdl(ce_kernel<false, STAGE>, dim3((unsigned)cdiv(T, warps)), dim3(warps * 32), 0, st, 
+        logits, ld, labels, rowmax, picked, sumexp, loss, grad, ldg, (__nv_bfloat16*)gradb, ldgb, T, V, cs, ce));
   } else {
-    ce_kernel<true, STAGE><<<(unsigned)T, 256, 0, st>>>(
-        logits, ld, labels, rowmax, picked, sumexp, loss, grad, ldg, (__nv_bfloat16*)gradb, ldgb, T, V, cs, ce);
+    NPT_CHECK_CUDA(launch_pdl(ce_kernel<true, STAGE>, dim3((unsigned)T), dim3(256), 0, st, 
+        logits, ld, labels, rowmax, picked, sumexp, loss, grad, ldg, (__nv_bfloat16*)gradb, ldgb, T, V, cs, ce));
   }
   NPT_LAUNCH_CHECK();
   return 0;
