@@ -121,11 +121,16 @@ colsum_stage1_kernel(const void* __restrict__ xv, int x_is_bf16, int64_t ld, flo
   }
 }
 // Vectorised stage 1: each thread owns 4 adjacent columns (16-byte fp32 / 8-byte bf16 loads),
-// block = 32 column groups (128 columns) x 8 row lanes, 4 rows in flight per lane.
+// block = 32 column groups (128 columns) x 8 row lanes, 4 rows in flight per lane.  The last block to
+// finish a 128-column strip (ticket counter per strip) adds the strip's partial rows in fixed order
+// and writes the result, so the sum does not depend on which block that is and no second launch is
+// needed.  The counters return to zero for the next launch (one stream at a time, like the workspace).
+__device__ unsigned int g_colsum_tickets[1024];
+
 template <bool BF16>
 __global__ void __launch_bounds__(256)
-colsum_stage1_vec_kernel(const void* __restrict__ xv, int64_t ld, float* __restrict__ partial, int64_t rows,
-                         int cols, int64_t rows_per_block) {
+colsum_stage1_vec_kernel(const void* __restrict__ xv, int64_t ld, float* __restrict__ partial, float* __restrict__ out,
+                         int64_t rows, int cols, int64_t rows_per_block) {
   pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
   pdl_trigger();
   __shared__ float4 sm[8][32];
@@ -164,6 +169,29 @@ colsum_stage1_vec_kernel(const void* __restrict__ xv, int64_t ld, float* __restr
     for (int k = 1; k < 8; ++k) { t.x += sm[k][cx].x; t.y += sm[k][cx].y; t.z += sm[k][cx].z; t.w += sm[k][cx].w; }
     *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * cols + col) = t;
   }
+  // ---- last block of the strip: final sum over the gridDim.y partial rows ----
+  __shared__ unsigned int ticket;
+  __threadfence();   // this block's partial row is visible device-wide before its ticket is drawn
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(&g_colsum_tickets[blockIdx.x], 1u);
+  __syncthreads();
+  if (ticket != gridDim.y - 1) return;
+  __threadfence();
+  acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < cols)
+    for (unsigned b = ry; b < gridDim.y; b += 8) {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(partial + (size_t)b * cols + col));
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  sm[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && col < cols) {
+    float4 t = sm[0][cx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { t.x += sm[k][cx].x; t.y += sm[k][cx].y; t.z += sm[k][cx].z; t.w += sm[k][cx].w; }
+    *reinterpret_cast<float4*>(out + col) = t;
+  }
+  if (threadIdx.x == 0) g_colsum_tickets[blockIdx.x] = 0;
 }
 
 // Stage 2: 32 columns x 32 row-lanes per block (independent loads), fixed-order smem tree.
@@ -257,11 +285,14 @@ int npt_colsum(const void* x, int32_t x_is_bf16, int64_t ld, float* out, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   const int parts = colsum_parts(rows, cols);
   const int64_t rpb = cdiv(rows, parts);
-  const bool vec = cols % 4 == 0 && ld % 4 == 0 && aligned16(workspace) && (x_is_bf16 ? aligned8(x) : aligned16(x));
-  if (vec) {
+  const bool vec = cols % 4 == 0 && ld % 4 == 0 && aligned16(workspace) && aligned16(out) && cols <= 1024 * 128 &&
+                   (x_is_bf16 ? aligned8(x) : aligned16(x));
+  if (vec) {  // single launch: the last block of each strip finishes the sum
     dim3 grid((unsigned)cdiv(cols, 128), (unsigned)parts);
-    if (x_is_bf16) NPT_CHECK_CUDA(launch_pdl(colsum_stage1_vec_kernel<true>, dim3(grid), dim3(256), 0, st, x, ld, (float*)workspace, rows, cols, rpb));
-    else NPT_CHECK_CUDA(launch_pdl(colsum_stage1_vec_kernel<false>, dim3(grid), dim3(256), 0, st, x, ld, (float*)workspace, rows, cols, rpb));
+    if (x_is_bf16) NPT_CHECK_CUDA(launch_pdl(colsum_stage1_vec_kernel<true>, dim3(grid), dim3(256), 0, st, x, ld, (float*)workspace, out, rows, cols, rpb));
+    else NPT_CHECK_CUDA(launch_pdl(colsum_stage1_vec_kernel<false>, dim3(grid), dim3(256), 0, st, x, ld, (float*)workspace, out, rows, cols, rpb));
+    NPT_LAUNCH_CHECK();
+    return 0;
   } else {
     dim3 grid((unsigned)cdiv(cols, 32), (unsigned)parts);
     NPT_CHECK_CUDA(launch_pdl(colsum_stage1_kernel, dim3(grid), dim3(256), 0, st, x, x_is_bf16, ld, (float*)workspace, rows, cols, rpb));

@@ -12,7 +12,10 @@ constexpr int kLnWarps = 8;      // rows per block
 constexpr int kLnMaxVec = 8;     // float4 per lane -> d <= 1024 on the register path
 
 // ---------------------------------------------------------------------------------------
-template <int NV>
+// EXACT: every operation rounded separately like NumPy (IEEE division per element) — the fp32 parity
+// mode.  !EXACT (a bf16 output is requested, i.e. the bf16 throughput mode): one reciprocal per row and a
+// multiply per element; the IEEE divisions were ~40 % of the instructions these kernels issue.
+template <int NV, bool EXACT>
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ residual,
@@ -50,6 +53,7 @@ ln_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   }
   const float var = warp_sum(q) / (float)d;
   const float denom = sqrtf(var + eps);
+  const float rden = __frcp_rn(denom);
   if (lane == 0) {
     mean_out[row] = mean;
     var_out[row] = var;
@@ -65,10 +69,17 @@ ln_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
       const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
       float4 o;
       // gamma * ((x - mean) / sqrt(var+eps)) + beta, each op rounded separately like NumPy.
-      o.x = __fadd_rn(__fmul_rn(g.x, __fdiv_rn(v[i].x - mean, denom)), b.x);
-      o.y = __fadd_rn(__fmul_rn(g.y, __fdiv_rn(v[i].y - mean, denom)), b.y);
-      o.z = __fadd_rn(__fmul_rn(g.z, __fdiv_rn(v[i].z - mean, denom)), b.z);
-      o.w = __fadd_rn(__fmul_rn(g.w, __fdiv_rn(v[i].w - mean, denom)), b.w);
+      if (EXACT) {
+        o.x = __fadd_rn(__fmul_rn(g.x, __fdiv_rn(v[i].x - mean, denom)), b.x);
+        o.y = __fadd_rn(__fmul_rn(g.y, __fdiv_rn(v[i].y - mean, denom)), b.y);
+        o.z = __fadd_rn(__fmul_rn(g.z, __fdiv_rn(v[i].z - mean, denom)), b.z);
+        o.w = __fadd_rn(__fmul_rn(g.w, __fdiv_rn(v[i].w - mean, denom)), b.w);
+      } else {
+        o.x = g.x * ((v[i].x - mean) * rden) + b.x;
+        o.y = g.y * ((v[i].y - mean) * rden) + b.y;
+        o.z = g.z * ((v[i].z - mean) * rden) + b.z;
+        o.w = g.w * ((v[i].w - mean) * rden) + b.w;
+      }
       if (r4) {
         const float4 r = ld_stream(r4 + c);
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -115,7 +126,7 @@ ln_fwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma
 
 // ---------------------------------------------------------------------------------------
 // Backward stage 1: dx per row + per-block partial dgamma/dbeta.
-template <int NV>
+template <int NV, bool EXACT>
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ mean_in, const float* __restrict__ var_in,
@@ -160,6 +171,7 @@ ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
         const float var = var_in[row];
         denom[u] = sqrtf(var + eps);
         stdv[u] = sqrtf(var);  // inputs.std(): no eps (normalization.py:48-50)
+        if (!EXACT) { denom[u] = __frcp_rn(denom[u]); stdv[u] = __frcp_rn(stdv[u]); }  // reciprocals
       }
     }
 #pragma unroll
@@ -173,8 +185,13 @@ ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
         if (c < nvec) {
           float4& xh = xv[u][i];  // becomes x-hat in place
           const float4 g4v = g[i], dd = dv[u][i];
-          xh.x = __fdiv_rn(xh.x - mean[u], denom[u]); xh.y = __fdiv_rn(xh.y - mean[u], denom[u]);
-          xh.z = __fdiv_rn(xh.z - mean[u], denom[u]); xh.w = __fdiv_rn(xh.w - mean[u], denom[u]);
+          if (EXACT) {
+            xh.x = __fdiv_rn(xh.x - mean[u], denom[u]); xh.y = __fdiv_rn(xh.y - mean[u], denom[u]);
+            xh.z = __fdiv_rn(xh.z - mean[u], denom[u]); xh.w = __fdiv_rn(xh.w - mean[u], denom[u]);
+          } else {
+            xh.x = (xh.x - mean[u]) * denom[u]; xh.y = (xh.y - mean[u]) * denom[u];
+            xh.z = (xh.z - mean[u]) * denom[u]; xh.w = (xh.w - mean[u]) * denom[u];
+          }
           ag[i].x += dd.x * xh.x; ag[i].y += dd.y * xh.y; ag[i].z += dd.z * xh.z; ag[i].w += dd.w * xh.w;
           ab[i].x += dd.x; ab[i].y += dd.y; ab[i].z += dd.z; ab[i].w += dd.w;
           float4& w = dv[u][i];   // becomes gamma*dy in place
@@ -191,10 +208,17 @@ ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
         if (c < nvec) {
           const float4 xh = xv[u][i], w = dv[u][i];
           float4 o;
-          o.x = __fdiv_rn(w.x - c1 * xh.x - c2, stdv[u]);
-          o.y = __fdiv_rn(w.y - c1 * xh.y - c2, stdv[u]);
-          o.z = __fdiv_rn(w.z - c1 * xh.z - c2, stdv[u]);
-          o.w = __fdiv_rn(w.w - c1 * xh.w - c2, stdv[u]);
+          if (EXACT) {
+            o.x = __fdiv_rn(w.x - c1 * xh.x - c2, stdv[u]);
+            o.y = __fdiv_rn(w.y - c1 * xh.y - c2, stdv[u]);
+            o.z = __fdiv_rn(w.z - c1 * xh.z - c2, stdv[u]);
+            o.w = __fdiv_rn(w.w - c1 * xh.w - c2, stdv[u]);
+          } else {
+            o.x = (w.x - c1 * xh.x - c2) * stdv[u];
+            o.y = (w.y - c1 * xh.y - c2) * stdv[u];
+            o.z = (w.z - c1 * xh.z - c2) * stdv[u];
+            o.w = (w.w - c1 * xh.w - c2) * stdv[u];
+          }
           if (dx) st_stream(outr + c, o);
           if (dxb) st_bf16x4(dxb + row * d + (int64_t)c * 4, o);
         }
@@ -295,8 +319,12 @@ static int launch_fwd(const float* x, const float* g, const float* b, const floa
                       void* yb, float* mean, float* var, int64_t rows, int d, float eps,
                       cudaStream_t st) {
   const int64_t grid = cdiv(rows, kLnWarps);
-  NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st, 
-      x, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
+  if (yb)  // bf16 throughput mode
+    NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, false>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
+        x, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
+  else
+    NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, true>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
+        x, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
   NPT_LAUNCH_CHECK();
   return 0;
 }
@@ -306,10 +334,15 @@ static int launch_bwd(const float* x, const float* g, const float* mean, const f
                       const float* dy, float* dx, void* dxb, float* partial, int nblocks,
                       int64_t rows, int d, float eps, cudaStream_t st) {
   const size_t smem = (size_t)kLnWarps * 2 * d * sizeof(float);
-  NPT_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_warp_kernel<NV>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NPT_CHECK_CUDA(launch_pdl(ln_bwd_warp_kernel<NV>, dim3(nblocks), dim3(kLnWarps * 32), smem, st, 
-      x, g, mean, var, dy, dx, (__nv_bfloat16*)dxb, partial, rows, d, eps));
+  if (dxb) {  // bf16 throughput mode
+    NPT_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_warp_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NPT_CHECK_CUDA(launch_pdl(ln_bwd_warp_kernel<NV, false>, dim3(nblocks), dim3(kLnWarps * 32), smem, st,
+        x, g, mean, var, dy, dx, (__nv_bfloat16*)dxb, partial, rows, d, eps));
+  } else {
+    NPT_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_warp_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NPT_CHECK_CUDA(launch_pdl(ln_bwd_warp_kernel<NV, true>, dim3(nblocks), dim3(kLnWarps * 32), smem, st,
+        x, g, mean, var, dy, dx, (__nv_bfloat16*)dxb, partial, rows, d, eps));
+  }
   NPT_LAUNCH_CHECK();
   return 0;
 }
