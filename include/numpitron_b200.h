@@ -107,6 +107,15 @@ int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, con
                       const float* dy, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
                       int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
                       void* stream);
+/* Same, plus dx_colsum[d] = column sums of dx (NULL: not wanted).  dx is the dy of the Linear layer
+ * in front of this LayerNorm (TransformerBlock.backward, nn/transformer_block.py:27-30), so this is
+ * that layer's bias gradient (nn/linear.py:57-58) without a second pass over dx.  Needs
+ * npt_layernorm_bwd_colsum_supported(d) (d % 4 == 0, d <= 1024). */
+int npt_layernorm_bwd_colsum_supported(int32_t d);
+int npt_layernorm_bwd_colsum(const float* x, const float* gamma, const float* mean, const float* var,
+                             const float* dy, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                             float* dx_colsum, int64_t rows, int32_t d, float eps, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* ---- ReLU — nn/activation.py:38-43 (stand-alone; the GEMM epilogue fuses both) ---------- */
 int npt_relu_fwd(const float* x, float* y, void* y_bf16, int64_t n, void* stream);

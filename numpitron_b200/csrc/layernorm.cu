@@ -126,7 +126,11 @@ ln_fwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma
 
 // ---------------------------------------------------------------------------------------
 // Backward stage 1: dx per row + per-block partial dgamma/dbeta.
-template <int NV, bool EXACT>
+// DXSUM: also accumulate the column sums of dx (third slice of the partials) — dx is the dy of the
+// Linear layer that precedes this LayerNorm, so this is that layer's bias gradient (nn/linear.py:57-58)
+// without a separate pass over dx.  The running sums live in shared memory (one slice per warp, each
+// lane owns its columns), not in registers: at 126 registers two blocks fit an SM, at 138 only one.
+template <int NV, bool EXACT, bool DXSUM>
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ mean_in, const float* __restrict__ var_in,
@@ -135,10 +139,17 @@ ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                    int64_t rows, int d, float eps) {
   pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
   pdl_trigger();
-  extern __shared__ float sm[];  // [kLnWarps][2][d]
+  extern __shared__ float sm[];  // [kLnWarps][NSL][d]
+  constexpr int NSL = DXSUM ? 3 : 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = d >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4* dsum = reinterpret_cast<float4*>(sm + ((size_t)warp * NSL + 2) * d);  // DXSUM: this warp's running sums
+  if (DXSUM) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + i * 32 < nvec) dsum[lane + i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float4 g[NV], ag[NV], ab[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -221,12 +232,17 @@ ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
           }
           if (dx) st_stream(outr + c, o);
           if (dxb) st_bf16x4(dxb + row * d + (int64_t)c * 4, o);
+          if (DXSUM) {
+            float4 t = dsum[c];
+            t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+            dsum[c] = t;
+          }
         }
       }
     }
   }
-  // combine the block's warps: smem [warp][2][d]
-  float* mine = sm + (size_t)warp * 2 * d;
+  // combine the block's warps: smem [warp][NSL][d]
+  float* mine = sm + (size_t)warp * NSL * d;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
@@ -236,11 +252,11 @@ ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+  for (int c = threadIdx.x; c < NSL * d; c += blockDim.x) {
     float t = 0.f;
 #pragma unroll
-    for (int w2 = 0; w2 < kLnWarps; ++w2) t += sm[(size_t)w2 * 2 * d + c];
-    partial[(size_t)blockIdx.x * 2 * d + c] = t;
+    for (int w2 = 0; w2 < kLnWarps; ++w2) t += sm[(size_t)w2 * NSL * d + c];
+    partial[(size_t)blockIdx.x * NSL * d + c] = t;
   }
 }
 
@@ -289,22 +305,22 @@ ln_bwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma
 // (independent loads in flight), then a fixed-order smem tree adds the 32 lanes.
 __global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out0,
-                       float* __restrict__ out1, int nblocks, int d) {
+                       float* __restrict__ out1, float* __restrict__ out2, int nsl, int nblocks, int d) {
   pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
   pdl_trigger();
   __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   float t = 0.f;
-  if (c < 2 * d)
-    for (int b = ry; b < nblocks; b += 32) t += partial[(size_t)b * 2 * d + c];
+  if (c < nsl * d)
+    for (int b = ry; b < nblocks; b += 32) t += partial[(size_t)b * nsl * d + c];
   sm[ry][cx] = t;
   __syncthreads();
-  if (ry == 0 && c < 2 * d) {
+  if (ry == 0 && c < nsl * d) {
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 32; ++k) s += sm[k][cx];
-    if (c < d) out0[c] = s; else out1[c - d] = s;
+    if (c < d) out0[c] = s; else if (c < 2 * d) out1[c - d] = s; else out2[c - 2 * d] = s;
   }
 }
 
@@ -329,22 +345,28 @@ static int launch_fwd(const float* x, const float* g, const float* b, const floa
   return 0;
 }
 
-template <int NV>
-static int launch_bwd(const float* x, const float* g, const float* mean, const float* var,
-                      const float* dy, float* dx, void* dxb, float* partial, int nblocks,
-                      int64_t rows, int d, float eps, cudaStream_t st) {
-  const size_t smem = (size_t)kLnWarps * 2 * d * sizeof(float);
-  if (dxb) {  // bf16 throughput mode
-    NPT_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_warp_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NPT_CHECK_CUDA(launch_pdl(ln_bwd_warp_kernel<NV, false>, dim3(nblocks), dim3(kLnWarps * 32), smem, st,
-        x, g, mean, var, dy, dx, (__nv_bfloat16*)dxb, partial, rows, d, eps));
-  } else {
-    NPT_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_warp_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NPT_CHECK_CUDA(launch_pdl(ln_bwd_warp_kernel<NV, true>, dim3(nblocks), dim3(kLnWarps * 32), smem, st,
-        x, g, mean, var, dy, dx, (__nv_bfloat16*)dxb, partial, rows, d, eps));
-  }
+template <int NV, bool EXACT, bool DXSUM>
+static int launch_bwd_k(const float* x, const float* g, const float* mean, const float* var, const float* dy, float* dx,
+                        void* dxb, float* partial, int nblocks, int64_t rows, int d, float eps, cudaStream_t st) {
+  const size_t smem = (size_t)kLnWarps * (DXSUM ? 3 : 2) * d * sizeof(float);
+  auto kern = ln_bwd_warp_kernel<NV, EXACT, DXSUM>;
+  NPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NPT_CHECK_CUDA(launch_pdl(kern, dim3(nblocks), dim3(kLnWarps * 32), smem, st, x, g, mean, var, dy, dx,
+                            (__nv_bfloat16*)dxb, partial, rows, d, eps));
   NPT_LAUNCH_CHECK();
   return 0;
+}
+
+template <int NV>
+static int launch_bwd(const float* x, const float* g, const float* mean, const float* var,
+                      const float* dy, float* dx, void* dxb, float* partial, bool dxsum, int nblocks,
+                      int64_t rows, int d, float eps, cudaStream_t st) {
+  if (dxb) {  // bf16 throughput mode
+    if (dxsum) return launch_bwd_k<NV, false, true>(x, g, mean, var, dy, dx, dxb, partial, nblocks, rows, d, eps, st);
+    return launch_bwd_k<NV, false, false>(x, g, mean, var, dy, dx, dxb, partial, nblocks, rows, d, eps, st);
+  }
+  if (dxsum) return launch_bwd_k<NV, true, true>(x, g, mean, var, dy, dx, dxb, partial, nblocks, rows, d, eps, st);
+  return launch_bwd_k<NV, true, false>(x, g, mean, var, dy, dx, dxb, partial, nblocks, rows, d, eps, st);
 }
 
 }  // namespace npt
@@ -382,13 +404,23 @@ int npt_layernorm_fwd(const float* x, const float* gamma, const float* beta, con
 size_t npt_layernorm_bwd_workspace_bytes(int64_t rows, int32_t d) {
   // sized for the larger of the two grid choices
   int64_t nb = (int64_t)sm_count() * 2;
-  return (size_t)nb * 2 * (size_t)d * sizeof(float);
+  return (size_t)nb * 3 * (size_t)d * sizeof(float);  // room for the optional dx column sums
 }
 
 int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, const float* var,
                       const float* dy, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
                       int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
                       void* stream) {
+  return npt_layernorm_bwd_colsum(x, gamma, mean, var, dy, dx, dx_bf16, dgamma, dbeta, nullptr, rows, d, eps, workspace,
+                                  workspace_bytes, stream);
+}
+
+int npt_layernorm_bwd_colsum_supported(int32_t d) { return (d % 4 == 0 && d <= kLnMaxVec * 128) ? 1 : 0; }
+
+int npt_layernorm_bwd_colsum(const float* x, const float* gamma, const float* mean, const float* var,
+                             const float* dy, float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum,
+                             int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
+                             void* stream) {
   NPT_REQUIRE(rows > 0 && d > 0, "layernorm_bwd: bad shape rows=%lld d=%d", (long long)rows, d);
   NPT_REQUIRE(dx || dx_bf16, "layernorm_bwd: no output");
   NPT_REQUIRE(workspace && workspace_bytes >= npt_layernorm_bwd_workspace_bytes(rows, d),
@@ -399,18 +431,21 @@ int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, con
   int nblocks;
   const bool vec = (d % 4 == 0) && d <= kLnMaxVec * 128 && aligned16(x) && aligned16(dy) &&
                    (!dx || aligned16(dx)) && aligned16(gamma) && (!dx_bf16 || aligned8(dx_bf16)) &&
-                   (size_t)kLnWarps * 2 * d * sizeof(float) <= 200 * 1024;
+                   (size_t)kLnWarps * 3 * d * sizeof(float) <= 200 * 1024;
+  const bool dxsum = dx_colsum != nullptr;
+  NPT_REQUIRE(!dxsum || vec, "layernorm_bwd: fused dx column sums need d %% 4 == 0, d <= %d and 16-byte aligned buffers",
+              kLnMaxVec * 128);
   if (vec) {
     nblocks = ln_bwd_blocks(rows);
     const int nv = (int)cdiv(d, 128);
     int rc;
     switch (nv) {
-      case 1: rc = launch_bwd<1>(x, gamma, mean, var, dy, dx, dx_bf16, partial, nblocks, rows, d, eps, st); break;
-      case 2: rc = launch_bwd<2>(x, gamma, mean, var, dy, dx, dx_bf16, partial, nblocks, rows, d, eps, st); break;
-      case 3: rc = launch_bwd<3>(x, gamma, mean, var, dy, dx, dx_bf16, partial, nblocks, rows, d, eps, st); break;
-      case 4: rc = launch_bwd<4>(x, gamma, mean, var, dy, dx, dx_bf16, partial, nblocks, rows, d, eps, st); break;
-      case 5: case 6: rc = launch_bwd<6>(x, gamma, mean, var, dy, dx, dx_bf16, partial, nblocks, rows, d, eps, st); break;
-      default: rc = launch_bwd<8>(x, gamma, mean, var, dy, dx, dx_bf16, partial, nblocks, rows, d, eps, st); break;
+      case 1: rc = launch_bwd<1>(x, gamma, mean, var, dy, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 2: rc = launch_bwd<2>(x, gamma, mean, var, dy, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 3: rc = launch_bwd<3>(x, gamma, mean, var, dy, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 4: rc = launch_bwd<4>(x, gamma, mean, var, dy, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 5: case 6: rc = launch_bwd<6>(x, gamma, mean, var, dy, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      default: rc = launch_bwd<8>(x, gamma, mean, var, dy, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
     }
     if (rc) return rc;
   } else {
@@ -420,7 +455,9 @@ int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, con
                                                   (__nv_bfloat16*)dx_bf16, partial, rows, d, eps));
     NPT_LAUNCH_CHECK();
   }
-  NPT_CHECK_CUDA(launch_pdl(reduce_partials_kernel, dim3((unsigned)cdiv(2 * (int64_t)d, 32)), dim3(1024), 0, st, partial, dgamma, dbeta, nblocks, d));
+  const int nsl = dxsum ? 3 : 2;
+  NPT_CHECK_CUDA(launch_pdl(reduce_partials_kernel, dim3((unsigned)cdiv(nsl * (int64_t)d, 32)), dim3(1024), 0, st, partial,
+                            dgamma, dbeta, dx_colsum, nsl, nblocks, d));
   NPT_LAUNCH_CHECK();
   return 0;
 }

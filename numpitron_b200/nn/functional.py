@@ -105,6 +105,10 @@ def linear_backward_input(dy, layer, wname="weight", mask=None, out="f32"):
 
 
 def bias_grad(dy):
-    """db = dy.sum(axis=(0,1)) — nn/linear.py:57-58 (reads fp32 or bf16)."""
+    """db = dy.sum(axis=(0,1)) — nn/linear.py:57-58 (reads fp32 or bf16).  When dy came out of
+    LayerNorm.backward the sums were already computed there (ops.layernorm_bwd, want_colsum)."""
+    fused = getattr(dy, "_npt_colsum", None)
+    if fused is not None:
+        return fused
     n = dy.shape[-1]
     return ops.colsum(dy.numel() // n, n, dy)

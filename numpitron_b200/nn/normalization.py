@@ -25,10 +25,12 @@ class LayerNorm(Layer):
 
     def backward(self, d_out, gemm_only: bool = False):
         """`gemm_only`: the caller feeds d_in straight into Linear.backward, so bf16 mode may return
-        it as a bf16 tensor alone."""
+        it as a bf16 tensor alone, and that layer's bias gradient (the column sums of d_in) is computed
+        here, in the pass that produces d_in."""
         inputs, mean, var = self.ctx.pop("inputs"), self.ctx.pop("mean"), self.ctx.pop("var")
         d_in, d_weight, d_bias = ops.layernorm_bwd(inputs, self.weight.data, mean, var, d_out, self.eps,
-                                                   want_bf16=rt.is_bf16(), bf16_only=gemm_only and rt.is_bf16())
+                                                   want_bf16=rt.is_bf16(), bf16_only=gemm_only and rt.is_bf16(),
+                                                   want_colsum=gemm_only)
         self.update_parameter("weight", gradient=d_weight)
         self.update_parameter("bias", gradient=d_bias)
         return d_in

@@ -112,23 +112,29 @@ def layernorm_fwd(x, gamma, beta, eps, residual=None, want_bf16=False):
     return y, mean, var
 
 
-def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False, bf16_only=False):
-    """Returns (dx, dgamma, dbeta); with bf16_only dx is a bf16 tensor (it only feeds GEMMs)."""
+def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False, bf16_only=False, want_colsum=False):
+    """Returns (dx, dgamma, dbeta); with bf16_only dx is a bf16 tensor (it only feeds GEMMs).
+    `want_colsum`: the column sums of dx (the bias gradient of the Linear in front of this LayerNorm) are
+    computed in the same pass and attached to the returned dx as `_npt_colsum` (nn.functional.bias_grad
+    picks them up)."""
     lib = _lib_()
     d = x.shape[-1]
     rows = x.numel() // d
     dx = None if bf16_only else rt.empty(x.shape)
     dxb = rt.empty(x.shape, _BF16) if (want_bf16 or bf16_only) else None
     dgamma, dbeta = rt.empty((d,)), rt.empty((d,))
+    colsum_out = rt.empty((d,)) if (want_colsum and lib.npt_layernorm_bwd_colsum_supported(d)) else None
     need = lib.npt_layernorm_bwd_workspace_bytes(rows, d)
     ws = rt.workspace(need)
-    check(lib.npt_layernorm_bwd(_p(x), _p(gamma), _p(mean), _p(var), _p(dy), _p(dx), _p(dxb), _p(dgamma), _p(dbeta),
-                                rows, d, eps, ws.data_ptr(), ws.numel(), rt.stream()), "npt_layernorm_bwd")
-    if bf16_only:
-        return dxb, dgamma, dbeta
-    if dxb is not None:
+    check(lib.npt_layernorm_bwd_colsum(_p(x), _p(gamma), _p(mean), _p(var), _p(dy), _p(dx), _p(dxb), _p(dgamma),
+                                       _p(dbeta), _p(colsum_out), rows, d, eps, ws.data_ptr(), ws.numel(), rt.stream()),
+          "npt_layernorm_bwd_colsum")
+    out = dxb if bf16_only else dx
+    if not bf16_only and dxb is not None:
         rt.attach_bf16(dx, dxb)
-    return dx, dgamma, dbeta
+    if colsum_out is not None:
+        out._npt_colsum = colsum_out
+    return out, dgamma, dbeta
 
 
 # ---- ReLU / column sum ---------------------------------------------------------------------------

@@ -319,6 +319,16 @@ def test_layernorm_shapes_vs_oracle(rows, d):
     close(host(dx), dx_ref, 1e-4)
     close(host(dg), dg_ref, 1e-4)
     close(host(db), db_ref, 1e-5)
+    if d % 4 == 0 and d <= 1024:
+        # fused bias gradient of the preceding Linear: column sums of dx from the same pass (fp32 parity
+        # mode and the bf16 throughput mode, whose dx differs by the reciprocal-multiply rounding only)
+        dx2, dg2, db2 = ops.layernorm_bwd(xt, dev(g), mean, var, dev(dy), 1e-5, want_colsum=True)
+        np.testing.assert_array_equal(host(dx2), host(dx))
+        np.testing.assert_array_equal(host(dg2), host(dg))
+        close(host(dx2._npt_colsum), dx_ref.reshape(rows, d).astype(np.float64).sum(0), 2e-4)
+        dx3, _, _ = ops.layernorm_bwd(xt, dev(g), mean, var, dev(dy), 1e-5, bf16_only=True, want_colsum=True)
+        close(host(dx3), dx_ref, 1e-2)
+        close(host(dx3._npt_colsum), dx_ref.reshape(rows, d).astype(np.float64).sum(0), 2e-4)
 
 
 def test_relu_colsum_golden(golden_layers):
