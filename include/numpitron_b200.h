@@ -78,7 +78,8 @@ typedef struct npt_gemm_args {
   int32_t mask_is_bf16;    /* dtype of mask */
   int64_t ldmask, stride_mask_outer, stride_mask_inner;
   void* workspace; size_t workspace_bytes;   /* split-K partials; see npt_gemm_workspace_bytes */
-  /* Packed ReLU mask (bf16 tensor-core mode, batch == 1): bit (n % 32) of word [m][n / 32].
+  /* Packed ReLU mask (bf16 tensor-core mode, batch == 1): bit (n % 32) of word [n / 32][m], i.e. the
+   * words are stored word-major with row pitch ld_bits >= M (32 consecutive rows = one 128-byte line).
    * relu_bits_out: written by a relu=1 GEMM (bit = output > 0); mask_bits: consumed like `mask`
    * by the backward GEMM — 1/16 of the bytes of a bf16 mask and no extra pass in the epilogue. */
   uint32_t* relu_bits_out; const uint32_t* mask_bits; int64_t ld_bits;

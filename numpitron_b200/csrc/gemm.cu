@@ -95,7 +95,7 @@ int npt_gemm(const npt_gemm_args* args, void* stream) {
   NPT_REQUIRE(!a.mask || a.ldmask >= a.N, "gemm: ldmask too small");
   if (a.relu_bits_out || a.mask_bits) {
     NPT_REQUIRE(a.mode == NPT_GEMM_BF16_TC && a.batch == 1, "gemm: packed ReLU bits need the bf16 tensor-core mode and batch == 1");
-    NPT_REQUIRE(a.ld_bits * 32 >= a.N, "gemm: ld_bits too small");
+    NPT_REQUIRE(a.ld_bits >= a.M, "gemm: ld_bits (row pitch of the word-major bit matrix) must be >= M");
     NPT_REQUIRE(!a.relu_bits_out || a.relu, "gemm: relu_bits_out needs relu = 1");
   }
   cudaStream_t st = (cudaStream_t)stream;

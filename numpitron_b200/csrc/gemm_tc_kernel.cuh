@@ -496,7 +496,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int nb = n0 + (half + 2 * pp) * 64 + h * 32;
-            mwords[pp][h] = (pp < npairs && m < M && nb < N) ? __ldg(bits_in + (int64_t)m * ld_bits + (nb >> 5)) : 0u;
+            mwords[pp][h] = (pp < npairs && m < M && nb < N) ? __ldg(bits_in + (int64_t)(nb >> 5) * ld_bits + m) : 0u;
           }
       }
       mbar_wait(tmem_full_bar + acc, (tile_i >> 1) & 1);
@@ -548,7 +548,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t w = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
-          if (inside && m < M) bits_out[(int64_t)m * ld_bits + (nb >> 5)] = w;
+          if (inside && m < M) bits_out[(int64_t)(nb >> 5) * ld_bits + m] = w;  // word-major: a warp's 32 rows are one 128-byte line
         }
         if (NPT_DBG(p, 1)) {
           float acc_dbg = 0.f;
@@ -646,7 +646,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (epi.bits_in) {
 #pragma unroll
         for (int cc = 0; cc < BN / 32; ++cc)
-          mwords[cc] = (m < p.M && n0 + cc * 32 < p.N) ? __ldg(epi.bits_in + (int64_t)m * epi.ld_bits + (n0 >> 5) + cc) : 0u;
+          mwords[cc] = (m < p.M && n0 + cc * 32 < p.N) ? __ldg(epi.bits_in + (int64_t)((n0 >> 5) + cc) * epi.ld_bits + m) : 0u;
       }
       mbar_wait(tmem_full_bar + acc, (tile_i >> 1) & 1);
       tc_fence_after();
@@ -739,7 +739,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t w = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
-            epi.bits_out[(int64_t)m * epi.ld_bits + (nb >> 5)] = w;
+            epi.bits_out[(int64_t)(nb >> 5) * epi.ld_bits + m] = w;
           }
         }
         // two staging slots per warp (a deeper ring — 3 fp32 / 6 bf16 slots — was measured: no gain)

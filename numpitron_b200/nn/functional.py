@@ -62,7 +62,7 @@ def relu_bits_supported(d_out: int) -> bool:
 
 def linear_forward(x, layer, wname="weight", bias=None, relu=False, out="f32", relu_bits=None):
     """y = x @ W (+ b) (ReLU) — nn/linear.py:44-47.  x (..., d_in), W (d_in, d_out).
-    `relu_bits`: optional int32 (T, ceil(d_out/32)) buffer that receives the packed (y > 0) mask."""
+    `relu_bits`: optional int32 (ceil(d_out/32), T) buffer that receives the packed (y > 0) mask."""
     W = getattr(layer, wname).data
     d_in, d_out = W.shape
     T = x.numel() // d_in

@@ -30,7 +30,7 @@ class MLP(Model):
         if F.relu_bits_supported(d_hidden):
             # 1 bit per element (hidden > 0), packed by the forward epilogue: the backward reads these
             # 3 MB instead of the 50 MB bf16 activation
-            bits = rt.empty((inputs.numel() // inputs.shape[-1], (d_hidden + 31) // 32), torch.int32)
+            bits = rt.empty(((d_hidden + 31) // 32, inputs.numel() // inputs.shape[-1]), torch.int32)  # word-major
         hidden = self.column_linear.forward(inputs, relu=True, out="bf16", relu_bits=bits)
         self.ctx["relu_mask"] = bits if bits is not None else hidden
         outputs = self.row_linear.forward(hidden)

@@ -179,11 +179,11 @@ def test_gemm_packed_relu_bits(M, K, N):
     w = dev(bf16_round(rng.standard_normal((K, N)) * 0.1)).bfloat16()
     bias = dev(rng.standard_normal(N).astype(np.float32))
     nw = (N + 31) // 32
-    bits = torch.full((M, nw), -1, dtype=torch.int32, device="cuda")
+    bits = torch.full((nw, M), -1, dtype=torch.int32, device="cuda")  # word-major: [n / 32][m]
     hb = rt.empty((M, N), torch.bfloat16)
     h = rt.empty((M, N))
     ops.gemm(x, w, M, N, K, lda=K, ldb=N, C_out=h, ldc=N, Cb_out=hb, ldcb=N, bias=bias, relu=True, relu_bits_out=bits, mode=1)
-    got = host(bits).view(np.uint32)
+    got = np.ascontiguousarray(host(bits).view(np.uint32).T)
     want = np.zeros((M, nw), np.uint32)
     pos = host(h) > 0
     for j in range(N):
