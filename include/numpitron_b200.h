@@ -108,15 +108,25 @@ int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, con
                       const float* dy, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
                       int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
                       void* stream);
-/* Same, plus dx_colsum[d] = column sums of dx (NULL: not wanted).  dx is the dy of the Linear layer
- * in front of this LayerNorm (TransformerBlock.backward, nn/transformer_block.py:27-30), so this is
- * that layer's bias gradient (nn/linear.py:57-58) without a second pass over dx.  Needs
- * npt_layernorm_bwd_colsum_supported(d) (d % 4 == 0, d <= 1024). */
+/* v2 entry points.  Additions over the calls above:
+ *  - x (and, in the backward, dy) may be bf16 (x_is_bf16 / inputs_are_bf16 = 1): in the bf16 throughput
+ *    mode the sub-layer output that LayerNorm normalises, and the dX that reaches its backward, come out
+ *    of a GEMM epilogue as bf16 alone — half the bytes to store, to all-reduce across tensor-parallel
+ *    ranks (nn/attention.py:57-58,101-102, nn/mlp.py:35-36,52-53) and to read here.  Needs
+ *    npt_layernorm_bf16_input_supported(d) (d % 4 == 0, d <= 1024).
+ *  - dx_colsum[d] (NULL: not wanted) = column sums of dx.  dx is the dy of the Linear layer in front of
+ *    this LayerNorm (TransformerBlock.backward, nn/transformer_block.py:27-30), so this is that layer's
+ *    bias gradient (nn/linear.py:57-58) without a second pass over dx.  Needs
+ *    npt_layernorm_bwd_colsum_supported(d). */
+int npt_layernorm_bf16_input_supported(int32_t d);
 int npt_layernorm_bwd_colsum_supported(int32_t d);
-int npt_layernorm_bwd_colsum(const float* x, const float* gamma, const float* mean, const float* var,
-                             const float* dy, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
-                             float* dx_colsum, int64_t rows, int32_t d, float eps, void* workspace,
-                             size_t workspace_bytes, void* stream);
+int npt_layernorm_fwd_v2(const void* x, int32_t x_is_bf16, const float* gamma, const float* beta,
+                         const float* residual, float* y, void* y_bf16, float* mean, float* var,
+                         int64_t rows, int32_t d, float eps, void* stream);
+int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16, const float* gamma,
+                         const float* mean, const float* var, float* dx, void* dx_bf16, float* dgamma,
+                         float* dbeta, float* dx_colsum, int64_t rows, int32_t d, float eps,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- ReLU — nn/activation.py:38-43 (stand-alone; the GEMM epilogue fuses both) ---------- */
 int npt_relu_fwd(const float* x, float* y, void* y_bf16, int64_t n, void* stream);

@@ -139,6 +139,7 @@ static TcConfig tc_config(const npt_gemm_args& a) {
   // measured (profiles/README.md): pairs win from N ~ 1024 up (16384x1536x384: 24.3 vs 26.8 us, 8192^3: 756 vs
   // 925 us) and lose on narrow outputs, where a launch is a couple of tiles per CTA and fixed costs dominate
   if (a.N < 1024 || m_tiles % 2 != 0 || !tc_fast_ok(a)) return best;
+  if (a.relu_bits_out) return best;  // bias + ReLU + bit packing: the pair's epilogue becomes the limit (27.8 vs 25.7 us)
   if (m_tiles * cdiv(a.N, best.bn) * a.batch * 2 <= sms) return best;  // split-K territory: single CTAs
   const char* env = getenv("NUMPITRON_GEMM_PAIR");
   if (env && env[0] == '0') return best;

@@ -15,9 +15,24 @@ constexpr int kLnMaxVec = 8;     // float4 per lane -> d <= 1024 on the register
 // EXACT: every operation rounded separately like NumPy (IEEE division per element) — the fp32 parity
 // mode.  !EXACT (a bf16 output is requested, i.e. the bf16 throughput mode): one reciprocal per row and a
 // multiply per element; the IEEE divisions were ~40 % of the instructions these kernels issue.
-template <int NV, bool EXACT>
+// MODE 0 = EXACT (fp32 input), 1 = fast (fp32 input), 2 = fast, bf16 input (x — and dy in the backward — come
+// from a GEMM epilogue as bf16 alone: half the bytes to write there, to all-reduce under tensor
+// parallelism and to read here).
+__device__ __forceinline__ float4 ld_bf16x4_stream(const void* p) {
+  const uint2 u = __ldcs(reinterpret_cast<const uint2*>(p));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <bool INBF>
+__device__ __forceinline__ float4 ln_load4(const void* base, int64_t row, int d, int c) {
+  if (INBF) return ld_bf16x4_stream(reinterpret_cast<const __nv_bfloat16*>(base) + row * d + (int64_t)c * 4);
+  return ld_stream(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + row * d) + c);
+}
+
+template <int NV, int MODE>
 __global__ void __launch_bounds__(kLnWarps * 32)
-ln_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+ln_fwd_warp_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ residual,
                    float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
                    float* __restrict__ mean_out, float* __restrict__ var_out,
@@ -27,15 +42,15 @@ ln_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.x * kLnWarps + warp;
   if (row >= rows) return;
+  constexpr bool EXACT = MODE == 0, INBF = MODE == 2;
   const int nvec = d >> 2;  // float4 per row
-  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
   float4 v[NV];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nvec) {
-      v[i] = ld_stream(xr + c);
+      v[i] = ln_load4<INBF>(x, row, d, c);
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -130,17 +145,18 @@ ln_fwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma
 // Linear layer that precedes this LayerNorm, so this is that layer's bias gradient (nn/linear.py:57-58)
 // without a separate pass over dx.  The running sums live in shared memory (one slice per warp, each
 // lane owns its columns), not in registers: at 126 registers two blocks fit an SM, at 138 only one.
-template <int NV, bool EXACT, bool DXSUM>
+template <int NV, int MODE, bool DXSUM>
 __global__ void __launch_bounds__(kLnWarps * 32)
-ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+ln_bwd_warp_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ mean_in, const float* __restrict__ var_in,
-                   const float* __restrict__ dy, float* __restrict__ dx,
+                   const void* __restrict__ dy, float* __restrict__ dx,
                    __nv_bfloat16* __restrict__ dxb, float* __restrict__ partial,
                    int64_t rows, int d, float eps) {
   pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
   pdl_trigger();
   extern __shared__ float sm[];  // [kLnWarps][NSL][d]
   constexpr int NSL = DXSUM ? 3 : 2;
+  constexpr bool EXACT = MODE == 0, INBF = MODE == 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = d >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
@@ -171,12 +187,10 @@ ln_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
       const int64_t row = row0 + u * stride;
       live[u] = row < rows;
       if (live[u]) {
-        const float4* xr = reinterpret_cast<const float4*>(x + row * d);
-        const float4* dr = reinterpret_cast<const float4*>(dy + row * d);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const int c = lane + i * 32;
-          if (c < nvec) { xv[u][i] = ld_stream(xr + c); dv[u][i] = ld_stream(dr + c); }
+          if (c < nvec) { xv[u][i] = ln_load4<INBF>(x, row, d, c); dv[u][i] = ln_load4<INBF>(dy, row, d, c); }
         }
         mean[u] = mean_in[row];
         const float var = var_in[row];
@@ -331,25 +345,28 @@ static int ln_bwd_blocks(int64_t rows) {
 }
 
 template <int NV>
-static int launch_fwd(const float* x, const float* g, const float* b, const float* r, float* y,
+static int launch_fwd(const void* x, bool in_bf16, const float* g, const float* b, const float* r, float* y,
                       void* yb, float* mean, float* var, int64_t rows, int d, float eps,
                       cudaStream_t st) {
   const int64_t grid = cdiv(rows, kLnWarps);
-  if (yb)  // bf16 throughput mode
-    NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, false>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
+  if (in_bf16)
+    NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, 2>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
+        x, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
+  else if (yb)  // bf16 throughput mode
+    NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, 1>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
         x, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
   else
-    NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, true>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
+    NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, 0>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
         x, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
   NPT_LAUNCH_CHECK();
   return 0;
 }
 
-template <int NV, bool EXACT, bool DXSUM>
-static int launch_bwd_k(const float* x, const float* g, const float* mean, const float* var, const float* dy, float* dx,
+template <int NV, int MODE, bool DXSUM>
+static int launch_bwd_k(const void* x, const float* g, const float* mean, const float* var, const void* dy, float* dx,
                         void* dxb, float* partial, int nblocks, int64_t rows, int d, float eps, cudaStream_t st) {
   const size_t smem = (size_t)kLnWarps * (DXSUM ? 3 : 2) * d * sizeof(float);
-  auto kern = ln_bwd_warp_kernel<NV, EXACT, DXSUM>;
+  auto kern = ln_bwd_warp_kernel<NV, MODE, DXSUM>;
   NPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NPT_CHECK_CUDA(launch_pdl(kern, dim3(nblocks), dim3(kLnWarps * 32), smem, st, x, g, mean, var, dy, dx,
                             (__nv_bfloat16*)dxb, partial, rows, d, eps));
@@ -358,15 +375,16 @@ static int launch_bwd_k(const float* x, const float* g, const float* mean, const
 }
 
 template <int NV>
-static int launch_bwd(const float* x, const float* g, const float* mean, const float* var,
-                      const float* dy, float* dx, void* dxb, float* partial, bool dxsum, int nblocks,
+static int launch_bwd(const void* x, const float* g, const float* mean, const float* var,
+                      const void* dy, bool in_bf16, float* dx, void* dxb, float* partial, bool dxsum, int nblocks,
                       int64_t rows, int d, float eps, cudaStream_t st) {
-  if (dxb) {  // bf16 throughput mode
-    if (dxsum) return launch_bwd_k<NV, false, true>(x, g, mean, var, dy, dx, dxb, partial, nblocks, rows, d, eps, st);
-    return launch_bwd_k<NV, false, false>(x, g, mean, var, dy, dx, dxb, partial, nblocks, rows, d, eps, st);
-  }
-  if (dxsum) return launch_bwd_k<NV, true, true>(x, g, mean, var, dy, dx, dxb, partial, nblocks, rows, d, eps, st);
-  return launch_bwd_k<NV, true, false>(x, g, mean, var, dy, dx, dxb, partial, nblocks, rows, d, eps, st);
+#define NPT_LN_BWD(MODE)                                                                                        \
+  return dxsum ? launch_bwd_k<NV, MODE, true>(x, g, mean, var, dy, dx, dxb, partial, nblocks, rows, d, eps, st) \
+               : launch_bwd_k<NV, MODE, false>(x, g, mean, var, dy, dx, dxb, partial, nblocks, rows, d, eps, st)
+  if (in_bf16) { NPT_LN_BWD(2); }
+  if (dxb) { NPT_LN_BWD(1); }  // bf16 throughput mode
+  NPT_LN_BWD(0);
+#undef NPT_LN_BWD
 }
 
 }  // namespace npt
@@ -378,25 +396,35 @@ extern "C" {
 int npt_layernorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual,
                       float* y, void* y_bf16, float* mean, float* var, int64_t rows, int32_t d,
                       float eps, void* stream) {
+  return npt_layernorm_fwd_v2(x, 0, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, stream);
+}
+
+int npt_layernorm_bf16_input_supported(int32_t d) { return (d % 4 == 0 && d <= kLnMaxVec * 128) ? 1 : 0; }
+
+int npt_layernorm_fwd_v2(const void* x, int32_t x_is_bf16, const float* gamma, const float* beta, const float* residual,
+                         float* y, void* y_bf16, float* mean, float* var, int64_t rows, int32_t d,
+                         float eps, void* stream) {
   NPT_REQUIRE(rows >= 0 && d > 0, "layernorm_fwd: bad shape rows=%lld d=%d", (long long)rows, d);
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool vec = (d % 4 == 0) && d <= kLnMaxVec * 128 && aligned16(x) && aligned16(y) &&
+  const bool vec = (d % 4 == 0) && d <= kLnMaxVec * 128 && (x_is_bf16 ? aligned8(x) : aligned16(x)) && aligned16(y) &&
                    aligned16(gamma) && aligned16(beta) && (!residual || aligned16(residual)) &&
                    (!y_bf16 || aligned8(y_bf16));
+  NPT_REQUIRE(!x_is_bf16 || vec, "layernorm_fwd: a bf16 input needs d %% 4 == 0, d <= %d and aligned buffers", kLnMaxVec * 128);
   if (vec) {
     const int nv = (int)cdiv(d, 128);
+    const bool ib = x_is_bf16 != 0;
     switch (nv) {
-      case 1: return launch_fwd<1>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      case 2: return launch_fwd<2>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      case 3: return launch_fwd<3>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      case 4: return launch_fwd<4>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      case 5: case 6: return launch_fwd<6>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      default: return launch_fwd<8>(x, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 1: return launch_fwd<1>(x, ib, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 2: return launch_fwd<2>(x, ib, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 3: return launch_fwd<3>(x, ib, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 4: return launch_fwd<4>(x, ib, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 5: case 6: return launch_fwd<6>(x, ib, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      default: return launch_fwd<8>(x, ib, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
     }
   }
-  NPT_CHECK_CUDA(launch_pdl(ln_fwd_block_kernel, dim3((unsigned)rows), dim3(256), 0, st, x, gamma, beta, residual, y,
-                                                      (__nv_bfloat16*)y_bf16, mean, var, rows, d, eps));
+  NPT_CHECK_CUDA(launch_pdl(ln_fwd_block_kernel, dim3((unsigned)rows), dim3(256), 0, st, (const float*)x, gamma, beta, residual, y,
+                            (__nv_bfloat16*)y_bf16, mean, var, rows, d, eps));
   NPT_LAUNCH_CHECK();
   return 0;
 }
@@ -411,16 +439,16 @@ int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, con
                       const float* dy, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
                       int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
                       void* stream) {
-  return npt_layernorm_bwd_colsum(x, gamma, mean, var, dy, dx, dx_bf16, dgamma, dbeta, nullptr, rows, d, eps, workspace,
-                                  workspace_bytes, stream);
+  return npt_layernorm_bwd_v2(x, dy, 0, gamma, mean, var, dx, dx_bf16, dgamma, dbeta, nullptr, rows, d, eps, workspace,
+                              workspace_bytes, stream);
 }
 
 int npt_layernorm_bwd_colsum_supported(int32_t d) { return (d % 4 == 0 && d <= kLnMaxVec * 128) ? 1 : 0; }
 
-int npt_layernorm_bwd_colsum(const float* x, const float* gamma, const float* mean, const float* var,
-                             const float* dy, float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum,
-                             int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
-                             void* stream) {
+int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16, const float* gamma, const float* mean,
+                         const float* var, float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum,
+                         int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
+                         void* stream) {
   NPT_REQUIRE(rows > 0 && d > 0, "layernorm_bwd: bad shape rows=%lld d=%d", (long long)rows, d);
   NPT_REQUIRE(dx || dx_bf16, "layernorm_bwd: no output");
   NPT_REQUIRE(workspace && workspace_bytes >= npt_layernorm_bwd_workspace_bytes(rows, d),
@@ -429,30 +457,31 @@ int npt_layernorm_bwd_colsum(const float* x, const float* gamma, const float* me
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = (float*)workspace;
   int nblocks;
-  const bool vec = (d % 4 == 0) && d <= kLnMaxVec * 128 && aligned16(x) && aligned16(dy) &&
+  const bool ib = inputs_are_bf16 != 0;
+  const bool vec = (d % 4 == 0) && d <= kLnMaxVec * 128 && (ib ? aligned8(x) && aligned8(dy) : aligned16(x) && aligned16(dy)) &&
                    (!dx || aligned16(dx)) && aligned16(gamma) && (!dx_bf16 || aligned8(dx_bf16)) &&
                    (size_t)kLnWarps * 3 * d * sizeof(float) <= 200 * 1024;
   const bool dxsum = dx_colsum != nullptr;
-  NPT_REQUIRE(!dxsum || vec, "layernorm_bwd: fused dx column sums need d %% 4 == 0, d <= %d and 16-byte aligned buffers",
-              kLnMaxVec * 128);
+  NPT_REQUIRE(!(dxsum || ib) || vec,
+              "layernorm_bwd: fused dx column sums / bf16 inputs need d %% 4 == 0, d <= %d and aligned buffers", kLnMaxVec * 128);
   if (vec) {
     nblocks = ln_bwd_blocks(rows);
     const int nv = (int)cdiv(d, 128);
     int rc;
     switch (nv) {
-      case 1: rc = launch_bwd<1>(x, gamma, mean, var, dy, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      case 2: rc = launch_bwd<2>(x, gamma, mean, var, dy, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      case 3: rc = launch_bwd<3>(x, gamma, mean, var, dy, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      case 4: rc = launch_bwd<4>(x, gamma, mean, var, dy, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      case 5: case 6: rc = launch_bwd<6>(x, gamma, mean, var, dy, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      default: rc = launch_bwd<8>(x, gamma, mean, var, dy, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 1: rc = launch_bwd<1>(x, gamma, mean, var, dy, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 2: rc = launch_bwd<2>(x, gamma, mean, var, dy, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 3: rc = launch_bwd<3>(x, gamma, mean, var, dy, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 4: rc = launch_bwd<4>(x, gamma, mean, var, dy, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 5: case 6: rc = launch_bwd<6>(x, gamma, mean, var, dy, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      default: rc = launch_bwd<8>(x, gamma, mean, var, dy, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
     }
     if (rc) return rc;
   } else {
     int64_t cap = (int64_t)sm_count() * 2;
     nblocks = (int)(rows < cap ? rows : cap);
-    NPT_CHECK_CUDA(launch_pdl(ln_bwd_block_kernel, dim3(nblocks), dim3(256), 0, st, x, gamma, mean, var, dy, dx,
-                                                  (__nv_bfloat16*)dx_bf16, partial, rows, d, eps));
+    NPT_CHECK_CUDA(launch_pdl(ln_bwd_block_kernel, dim3(nblocks), dim3(256), 0, st, (const float*)x, gamma, mean, var,
+                              (const float*)dy, dx, (__nv_bfloat16*)dx_bf16, partial, rows, d, eps));
     NPT_LAUNCH_CHECK();
   }
   const int nsl = dxsum ? 3 : 2;

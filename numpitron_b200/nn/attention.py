@@ -47,7 +47,8 @@ class Attention(Model):
             rt.attach_bf16(t, sh)
         return sh
 
-    def forward(self, inputs):
+    def forward(self, inputs, out: str = "f32"):
+        """`out`: dtype of the returned tensor in bf16 mode ("bf16" when it only feeds a LayerNorm)."""
         batch_size, seq_len, d_model = inputs.shape
         h = self._local_heads()
         bf16 = rt.is_bf16()
@@ -61,7 +62,7 @@ class Attention(Model):
         if bf16 and ops.attention_supported(seq_len, dh):
             # fused tcgen05 attention: scores / probabilities never leave the SM
             att_b, lse = ops.attention_fwd(qkv, batch_size, seq_len, h, dh, divisor)
-            outputs = self.out_projection.forward(att_b)
+            outputs = self.out_projection.forward(att_b, out=out)
             self.ctx |= {"qkv": qkv, "att": att_b, "lse": lse, "divisor": divisor,
                          "shape": (batch_size, seq_len, h, dh)}
             if self.is_scattered and npdist.tensor_parallel_size() > 1:
@@ -85,21 +86,21 @@ class Attention(Model):
         ops.gemm(p_op, q_op, seq_len, dh, seq_len, lda=seq_len, ldb=ld, b_off=2 * dh, a_strides=mat,
                  b_strides=head, C_out=att, ldc=h * dh, c_strides=merged,
                  Cb_out=att_b, ldcb=h * dh, cb_strides=merged, batch=nb, batch_inner=h)
-        outputs = self.out_projection.forward(att_b if bf16 else att)
+        outputs = self.out_projection.forward(att_b if bf16 else att, out=out)
 
         self.ctx |= {"qkv": qkv, "attention_weights": attention_weights, "shape": (batch_size, seq_len, h, dh)}
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
             npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
         return outputs
 
-    def backward(self, d_out):
+    def backward(self, d_out, out: str = "f32"):
         batch_size, seq_len, h, dh = self.ctx.pop("shape")
         qkv = self.ctx.pop("qkv")
         if "lse" in self.ctx:  # fused path
             att_b, lse, divisor = self.ctx.pop("att"), self.ctx.pop("lse"), self.ctx.pop("divisor")
             d_att = self.out_projection.backward(d_out, out="bf16")
             d_qkv = ops.attention_bwd(qkv, att_b, d_att, lse, batch_size, seq_len, h, dh, divisor)
-            return self._qkv_backward(d_qkv)
+            return self._qkv_backward(d_qkv, out)
         p = self.ctx.pop("attention_weights")
         bf16 = rt.is_bf16()
         ld = h * 3 * dh
@@ -132,15 +133,15 @@ class Attention(Model):
                  batch=nb, batch_inner=h, **into_qkv(0))
         ops.gemm(ds_op, qkv_op, seq_len, dh, seq_len, lda=seq_len, ldb=ld, trans_a=True, b_off=0, a_strides=mat,
                  b_strides=head, batch=nb, batch_inner=h, **into_qkv(dh))
-        return self._qkv_backward(d_qkv_b if bf16 else d_qkv)
+        return self._qkv_backward(d_qkv_b if bf16 else d_qkv, out)
 
-    def _qkv_backward(self, d_qkv):
+    def _qkv_backward(self, d_qkv, out: str = "f32"):
         """QKV-projection backward; under TP the all-reduce of dX (attention.py:101-102) is started as
         soon as dX is enqueued and overlaps the dW GEMM."""
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
             pending = []
             d_in = self.qkv_projection.backward(
-                d_qkv, on_dx=lambda dx: pending.append(npdist.all_reduce_async(dx, group=npdist.tensor_parallel_group())))
+                d_qkv, out=out, on_dx=lambda dx: pending.append(npdist.all_reduce_async(dx, group=npdist.tensor_parallel_group())))
             pending[0].wait()
             return d_in
-        return self.qkv_projection.backward(d_qkv)
+        return self.qkv_projection.backward(d_qkv, out=out)

@@ -22,7 +22,8 @@ class MLP(Model):
         # Only TP rank 0 adds the row-linear bias (mlp.py:35); the parameter exists everywhere.
         self.row_linear.use_bias = npdist.tensor_parallel_rank() == 0
 
-    def forward(self, inputs):
+    def forward(self, inputs, out: str = "f32"):
+        # `out`: dtype of the returned tensor in bf16 mode ("bf16" when it only feeds a LayerNorm).
         # max(0, x@W1+b1) in one GEMM epilogue; the post-ReLU tensor doubles as the backward mask
         # because relu(a) > 0  <=>  a > 0.  It only feeds GEMMs, so bf16 mode keeps it in bf16 alone.
         d_hidden = self.column_linear.weight.data.shape[1]
@@ -33,18 +34,18 @@ class MLP(Model):
             bits = rt.empty(((d_hidden + 31) // 32, inputs.numel() // inputs.shape[-1]), torch.int32)  # word-major
         hidden = self.column_linear.forward(inputs, relu=True, out="bf16", relu_bits=bits)
         self.ctx["relu_mask"] = bits if bits is not None else hidden
-        outputs = self.row_linear.forward(hidden)
+        outputs = self.row_linear.forward(hidden, out=out)
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
             npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
         return outputs
 
-    def backward(self, d_out):
+    def backward(self, d_out, out: str = "f32"):
         d_out = self.row_linear.backward(d_out, mask=self.ctx.pop("relu_mask"), out="bf16")  # (dy@W2^T) * (a>0)
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
             # all-reduce of dX (mlp.py:52-53) overlapped with the column-linear dW / db kernels
             pending = []
             d_out = self.column_linear.backward(
-                d_out, on_dx=lambda dx: pending.append(npdist.all_reduce_async(dx, group=npdist.tensor_parallel_group())))
+                d_out, out=out, on_dx=lambda dx: pending.append(npdist.all_reduce_async(dx, group=npdist.tensor_parallel_group())))
             pending[0].wait()
             return d_out
-        return self.column_linear.backward(d_out)
+        return self.column_linear.backward(d_out, out=out)

@@ -25,6 +25,9 @@ class Transformer(Model):
         """Reverse pass; after each TOP-LEVEL layer its own parameters are all-reduced (SUM) over the
         data-parallel group — which in practice is only the tied embedding gradient, because a
         TransformerBlock's own `parameters` dict is empty (reference: transformer.py:48-59, Q11)."""
+        blocks = [layer for layer in self.layers.values() if isinstance(layer, TransformerBlock)]
+        if blocks:
+            blocks[0].input_grad_f32 = True  # its dX goes to the embedding layers (fp32 readers)
         for layer in list(self.layers.values())[::-1]:
             d_out = layer.backward(d_out)
             if npdist.data_parallel_size() > 1:

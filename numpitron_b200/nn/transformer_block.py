@@ -1,6 +1,8 @@
 """TransformerBlock — drop-in for the reference's nn/transformer_block.py (quirks Q1/Q2 kept)."""
 from __future__ import annotations
 
+from .. import ops
+from .. import runtime as rt
 from .attention import Attention
 from .mlp import MLP
 from .model import Model
@@ -16,15 +18,28 @@ class TransformerBlock(Model):
         self.add_layer("norm2", LayerNorm(d_model, **kwargs))
         self.add_layer("mlp", MLP(d_model, d_model * 4, d_model, **kwargs))
 
+    # Set by Transformer.backward on the first block: its input gradient feeds the embedding layers,
+    # which read fp32.
+    input_grad_f32 = False
+
+    def _sub_dtype(self) -> str:
+        """bf16 mode: the sub-layer outputs LayerNorm normalises, and the dX that reaches a LayerNorm's
+        backward, leave their GEMM as bf16 alone (the residual stream itself stays fp32): half the bytes to
+        store, to all-reduce across tensor-parallel ranks and for LayerNorm to read."""
+        return "bf16" if rt.is_bf16() and ops.layernorm_bf16_input_supported(self.d_model) else "f32"
+
     def forward(self, inputs):
         # LayerNorm is applied to the SUB-LAYER OUTPUT, then the residual is added (Q1); the add is
         # fused into the LayerNorm kernel.
-        outputs = self.norm1.forward(self.attention(inputs), residual=inputs)
-        outputs = self.norm2.forward(self.mlp(outputs), residual=outputs)
+        sub = self._sub_dtype()
+        outputs = self.norm1.forward(self.attention.forward(inputs, out=sub), residual=inputs)
+        outputs = self.norm2.forward(self.mlp.forward(outputs, out=sub), residual=outputs)
         return outputs
 
     def backward(self, d_out):
         # The residual gradient is dropped, exactly as the reference does (Q2).
-        d_out = self.mlp.backward(self.norm2.backward(d_out, gemm_only=True))
-        d_out = self.attention.backward(self.norm1.backward(d_out, gemm_only=True))
+        sub = self._sub_dtype()
+        d_out = self.mlp.backward(self.norm2.backward(d_out, gemm_only=True), out=sub)
+        d_out = self.attention.backward(self.norm1.backward(d_out, gemm_only=True),
+                                        out="f32" if self.input_grad_f32 else sub)
         return d_out

@@ -98,15 +98,20 @@ def cast_bf16(t: torch.Tensor, pad_cols: bool = False) -> torch.Tensor:
 
 
 # ---- LayerNorm -----------------------------------------------------------------------------------
+def layernorm_bf16_input_supported(d: int) -> bool:
+    return bool(_lib_().npt_layernorm_bf16_input_supported(int(d)))
+
+
 def layernorm_fwd(x, gamma, beta, eps, residual=None, want_bf16=False):
+    """x: fp32, or bf16 (a sub-layer output that came out of its GEMM epilogue as bf16 alone)."""
     lib = _lib_()
     d = x.shape[-1]
     rows = x.numel() // d
     y = rt.empty(x.shape)
     yb = rt.empty(x.shape, _BF16) if want_bf16 else None
     mean, var = rt.empty((rows,)), rt.empty((rows,))
-    check(lib.npt_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(residual), _p(y), _p(yb), _p(mean), _p(var),
-                                rows, d, eps, rt.stream()), "npt_layernorm_fwd")
+    check(lib.npt_layernorm_fwd_v2(_p(x), int(x.dtype == _BF16), _p(gamma), _p(beta), _p(residual), _p(y), _p(yb),
+                                   _p(mean), _p(var), rows, d, eps, rt.stream()), "npt_layernorm_fwd_v2")
     if yb is not None:
         rt.attach_bf16(y, yb)
     return y, mean, var
@@ -126,9 +131,15 @@ def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False, bf16_only=False
     colsum_out = rt.empty((d,)) if (want_colsum and lib.npt_layernorm_bwd_colsum_supported(d)) else None
     need = lib.npt_layernorm_bwd_workspace_bytes(rows, d)
     ws = rt.workspace(need)
-    check(lib.npt_layernorm_bwd_colsum(_p(x), _p(gamma), _p(mean), _p(var), _p(dy), _p(dx), _p(dxb), _p(dgamma),
-                                       _p(dbeta), _p(colsum_out), rows, d, eps, ws.data_ptr(), ws.numel(), rt.stream()),
-          "npt_layernorm_bwd_colsum")
+    # x (the saved LayerNorm input) and dy are read as one dtype: both bf16 when either is
+    in_bf16 = x.dtype == _BF16 or dy.dtype == _BF16
+    if in_bf16 and x.dtype != _BF16:
+        x = cast_bf16(x)
+    if in_bf16 and dy.dtype != _BF16:
+        dy = cast_bf16(dy)
+    check(lib.npt_layernorm_bwd_v2(_p(x), _p(dy), int(in_bf16), _p(gamma), _p(mean), _p(var), _p(dx), _p(dxb),
+                                   _p(dgamma), _p(dbeta), _p(colsum_out), rows, d, eps, ws.data_ptr(), ws.numel(),
+                                   rt.stream()), "npt_layernorm_bwd_v2")
     out = dxb if bf16_only else dx
     if not bf16_only and dxb is not None:
         rt.attach_bf16(dx, dxb)

@@ -86,6 +86,8 @@ def from_numpy(a: np.ndarray) -> torch.Tensor:
 def to_numpy(t) -> np.ndarray:
     if t is None or isinstance(t, np.ndarray):
         return t
+    if t.dtype == torch.bfloat16:  # bf16-only activations / gradients of the bf16 mode: NumPy has no bf16
+        t = t.float()
     return t.detach().cpu().numpy()
 
 

@@ -329,6 +329,19 @@ def test_layernorm_shapes_vs_oracle(rows, d):
         dx3, _, _ = ops.layernorm_bwd(xt, dev(g), mean, var, dev(dy), 1e-5, bf16_only=True, want_colsum=True)
         close(host(dx3), dx_ref, 1e-2)
         close(host(dx3._npt_colsum), dx_ref.reshape(rows, d).astype(np.float64).sum(0), 2e-4)
+        # bf16 inputs (sub-layer output / dX that left their GEMM as bf16 alone): same math on the rounded values
+        xb, dyb = bf16_round(x), bf16_round(dy)
+        yb_ref, ctxb = O.layernorm_forward(xb, g, b)
+        dxb_ref, dgb_ref, dbb_ref = O.layernorm_backward(ctxb, g, dyb)
+        y4, mean4, var4 = ops.layernorm_fwd(dev(xb).bfloat16(), dev(g), dev(b), 1e-5, residual=dev(res), want_bf16=True)
+        close(host(y4), yb_ref + res, 2e-5)
+        dx4, dg4, db4 = ops.layernorm_bwd(dev(xb).bfloat16(), dev(g), mean4, var4, dev(dyb).bfloat16(), 1e-5, want_colsum=True)
+        close(host(dx4), dxb_ref, 1e-4)
+        close(host(dg4), dgb_ref, 1e-4)
+        close(host(db4), dbb_ref, 1e-5)
+        close(host(dx4._npt_colsum), dxb_ref.reshape(rows, d).astype(np.float64).sum(0), 2e-4)
+        dx5, _, _ = ops.layernorm_bwd(dev(xb).bfloat16(), dev(g), mean4, var4, dev(dyb), 1e-5)   # mixed: dy is cast
+        np.testing.assert_array_equal(host(dx5), host(dx4))
 
 
 def test_relu_colsum_golden(golden_layers):
