@@ -63,6 +63,39 @@ splitk_reduce_kernel(const float* __restrict__ partial, GemmEpilogue e, int spli
   }
 }
 
+// N % 4 == 0: one thread per float4 of the output, indexed (column quad, row, batch) by the grid — no
+// divisions (the generic kernel above spends two 64-bit divisions per element on them), four
+// independent partial loads in flight per thread, the additions in split order 0..S-1 as before.
+__global__ void __launch_bounds__(256)
+splitk_reduce_vec_kernel(const float* __restrict__ partial, GemmEpilogue e, int splits, int batch) {
+  pdl_wait();
+  pdl_trigger();
+  const int n = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int m = blockIdx.y * 8 + threadIdx.y;
+  const int b = blockIdx.z;
+  if (n >= e.N || m >= e.M) return;
+  const int64_t mn = (int64_t)e.M * e.N;
+  const int64_t stride = (int64_t)batch * mn;
+  const float* p0 = partial + (int64_t)b * mn + (int64_t)m * e.N + n;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s = 0;
+  for (; s + 4 <= splits; s += 4) {
+    const float4 a0 = __ldcs(reinterpret_cast<const float4*>(p0 + (int64_t)s * stride));
+    const float4 a1 = __ldcs(reinterpret_cast<const float4*>(p0 + (int64_t)(s + 1) * stride));
+    const float4 a2 = __ldcs(reinterpret_cast<const float4*>(p0 + (int64_t)(s + 2) * stride));
+    const float4 a3 = __ldcs(reinterpret_cast<const float4*>(p0 + (int64_t)(s + 3) * stride));
+    acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;
+    acc.x += a1.x; acc.y += a1.y; acc.z += a1.z; acc.w += a1.w;
+    acc.x += a2.x; acc.y += a2.y; acc.z += a2.z; acc.w += a2.w;
+    acc.x += a3.x; acc.y += a3.y; acc.z += a3.z; acc.w += a3.w;
+  }
+  for (; s < splits; ++s) {
+    const float4 a0 = __ldcs(reinterpret_cast<const float4*>(p0 + (int64_t)s * stride));
+    acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;
+  }
+  epi_store4(e, b, m, n, acc);
+}
+
 static int choose_splits(const npt_gemm_args& a) {
   if (a.mode == NPT_GEMM_FP32_SIMT) return gemm_simt_splits(a);
   return gemm_tc_splits(a);
@@ -116,6 +149,12 @@ int npt_gemm(const npt_gemm_args* args, void* stream) {
                                           : gemm_tc_launch(a, epi, splits, partial, st);
   if (rc) return rc;
   if (splits > 1) {
+    if (a.N % 4 == 0 && aligned16(partial) && a.batch <= 65535 && cdiv(a.M, 8) <= 65535) {
+      dim3 grid((unsigned)cdiv(a.N / 4, 32), (unsigned)cdiv(a.M, 8), (unsigned)a.batch);
+      NPT_CHECK_CUDA(launch_pdl(splitk_reduce_vec_kernel, grid, dim3(32, 8), 0, st, partial, epi, splits, a.batch));
+      NPT_LAUNCH_CHECK();
+      return 0;
+    }
     const int64_t total4 = ((int64_t)a.batch * a.M * a.N + 3) / 4;
     int64_t blocks = cdiv(total4, 256);
     const int64_t cap = (int64_t)sm_count() * 8;
