@@ -34,6 +34,14 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+def gemm_traffic(precision: str, n_gpus: int):
+    """Average DRAM bytes per GEMM launch of the step, from the committed ncu capture (bf16, 1 GPU only)."""
+    f = ROOT / "profiles" / "r01_gemm_dram_traffic.json"
+    if precision != "bf16" or n_gpus != 1 or not f.exists():
+        return None
+    return json.loads(f.read_text())["avg_dram_bytes_per_launch"]
+
+
 MODEL = dict(d_model=384, n_heads=6, n_layers=6, vocab_size=65, seq_len=256)
 SEQS_PER_GPU = 64
 LR, BETA1, BETA2 = 1e-4, 0.9, 0.99
@@ -296,7 +304,7 @@ def run_ours(args):
         peak = pk["bf16_burst"]
         roof = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None,
+            "traffic": gemm_traffic(args.precision, n_gpus),
             "kernel": "gemm_tc_kernel (tcgen05.mma + TMA)" if tc else "gemm_simt_kernel (fp32 FFMA)",
             "launches": len(prof), "ms_per_step_in_kernel": tot_ms, "flop_per_step": tot_flops,
             "peak_source": f"{pk['src']} bf16 burst (kernel timed alone, launch by launch)",

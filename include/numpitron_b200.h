@@ -117,16 +117,23 @@ int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, con
  *  - dx_colsum[d] (NULL: not wanted) = column sums of dx.  dx is the dy of the Linear layer in front of
  *    this LayerNorm (TransformerBlock.backward, nn/transformer_block.py:27-30), so this is that layer's
  *    bias gradient (nn/linear.py:57-58) without a second pass over dx.  Needs
- *    npt_layernorm_bwd_colsum_supported(d). */
+ *    npt_layernorm_bwd_colsum_supported(d).
+ *  - x_peer / dy_peer (NULL: none; bf16 inputs only): the OTHER tensor-parallel rank's partial of the same
+ *    tensor, a peer-memory pointer (NVLink P2P).  The kernel normalises round_bf16(x + x_peer), i.e. what
+ *    the reference's Allreduce (nn/attention.py:57-58, nn/mlp.py:35-36; backward: attention.py:101-102,
+ *    mlp.py:52-53) would have produced, without an all-reduce kernel in between; x_sum_bf16 (optional)
+ *    receives that reduced input for the backward pass.  tp = 2 only; the caller synchronises the two
+ *    ranks (both partials complete and visible) before the launch. */
 int npt_layernorm_bf16_input_supported(int32_t d);
 int npt_layernorm_bwd_colsum_supported(int32_t d);
-int npt_layernorm_fwd_v2(const void* x, int32_t x_is_bf16, const float* gamma, const float* beta,
-                         const float* residual, float* y, void* y_bf16, float* mean, float* var,
-                         int64_t rows, int32_t d, float eps, void* stream);
-int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16, const float* gamma,
-                         const float* mean, const float* var, float* dx, void* dx_bf16, float* dgamma,
-                         float* dbeta, float* dx_colsum, int64_t rows, int32_t d, float eps,
-                         void* workspace, size_t workspace_bytes, void* stream);
+int npt_layernorm_fwd_v2(const void* x, int32_t x_is_bf16, const void* x_peer, void* x_sum_bf16,
+                         const float* gamma, const float* beta, const float* residual, float* y,
+                         void* y_bf16, float* mean, float* var, int64_t rows, int32_t d, float eps,
+                         void* stream);
+int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16, const void* dy_peer,
+                         const float* gamma, const float* mean, const float* var, float* dx,
+                         void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int64_t rows,
+                         int32_t d, float eps, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- ReLU — nn/activation.py:38-43 (stand-alone; the GEMM epilogue fuses both) ---------- */
 int npt_relu_fwd(const float* x, float* y, void* y_bf16, int64_t n, void* stream);

@@ -30,9 +30,25 @@ __device__ __forceinline__ float4 ln_load4(const void* base, int64_t row, int d,
   return ld_stream(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + row * d) + c);
 }
 
+// Tensor parallelism over 2 ranks without an all-reduce kernel: `peer` is the other rank's partial
+// tensor (a peer-memory pointer over NVLink).  The sum is rounded to bf16 — exactly what a bf16
+// all-reduce would have left in memory — so both ranks, and the forward and backward passes, see
+// identical values.
+template <bool INBF>
+__device__ __forceinline__ float4 ln_load4_sum(const void* base, const void* peer, int64_t row, int d, int c) {
+  float4 a = ln_load4<INBF>(base, row, d, c);
+  if (INBF && peer) {
+    const float4 b = ln_load4<INBF>(peer, row, d, c);
+    a.x = __bfloat162float(__float2bfloat16_rn(a.x + b.x)); a.y = __bfloat162float(__float2bfloat16_rn(a.y + b.y));
+    a.z = __bfloat162float(__float2bfloat16_rn(a.z + b.z)); a.w = __bfloat162float(__float2bfloat16_rn(a.w + b.w));
+  }
+  return a;
+}
+
 template <int NV, int MODE>
 __global__ void __launch_bounds__(kLnWarps * 32)
-ln_fwd_warp_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
+ln_fwd_warp_kernel(const void* __restrict__ x, const void* __restrict__ x_peer, __nv_bfloat16* __restrict__ x_sum,
+                   const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ residual,
                    float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
                    float* __restrict__ mean_out, float* __restrict__ var_out,
@@ -50,7 +66,8 @@ ln_fwd_warp_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
   for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nvec) {
-      v[i] = ln_load4<INBF>(x, row, d, c);
+      v[i] = ln_load4_sum<INBF>(x, x_peer, row, d, c);
+      if (INBF && x_sum) st_bf16x4(x_sum + row * d + (int64_t)c * 4, v[i]);  // the reduced input, kept for the backward
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -149,7 +166,7 @@ template <int NV, int MODE, bool DXSUM>
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln_bwd_warp_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ mean_in, const float* __restrict__ var_in,
-                   const void* __restrict__ dy, float* __restrict__ dx,
+                   const void* __restrict__ dy, const void* __restrict__ dy_peer, float* __restrict__ dx,
                    __nv_bfloat16* __restrict__ dxb, float* __restrict__ partial,
                    int64_t rows, int d, float eps) {
   pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
@@ -190,7 +207,7 @@ ln_bwd_warp_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const int c = lane + i * 32;
-          if (c < nvec) { xv[u][i] = ln_load4<INBF>(x, row, d, c); dv[u][i] = ln_load4<INBF>(dy, row, d, c); }
+          if (c < nvec) { xv[u][i] = ln_load4<INBF>(x, row, d, c); dv[u][i] = ln_load4_sum<INBF>(dy, dy_peer, row, d, c); }
         }
         mean[u] = mean_in[row];
         const float var = var_in[row];
@@ -345,30 +362,30 @@ static int ln_bwd_blocks(int64_t rows) {
 }
 
 template <int NV>
-static int launch_fwd(const void* x, bool in_bf16, const float* g, const float* b, const float* r, float* y,
+static int launch_fwd(const void* x, bool in_bf16, const void* xp, void* xs, const float* g, const float* b, const float* r, float* y,
                       void* yb, float* mean, float* var, int64_t rows, int d, float eps,
                       cudaStream_t st) {
   const int64_t grid = cdiv(rows, kLnWarps);
   if (in_bf16)
     NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, 2>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
-        x, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
+        x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
   else if (yb)  // bf16 throughput mode
     NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, 1>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
-        x, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
+        x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
   else
     NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, 0>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
-        x, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
+        x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
   NPT_LAUNCH_CHECK();
   return 0;
 }
 
 template <int NV, int MODE, bool DXSUM>
-static int launch_bwd_k(const void* x, const float* g, const float* mean, const float* var, const void* dy, float* dx,
+static int launch_bwd_k(const void* x, const float* g, const float* mean, const float* var, const void* dy, const void* dyp, float* dx,
                         void* dxb, float* partial, int nblocks, int64_t rows, int d, float eps, cudaStream_t st) {
   const size_t smem = (size_t)kLnWarps * (DXSUM ? 3 : 2) * d * sizeof(float);
   auto kern = ln_bwd_warp_kernel<NV, MODE, DXSUM>;
   NPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NPT_CHECK_CUDA(launch_pdl(kern, dim3(nblocks), dim3(kLnWarps * 32), smem, st, x, g, mean, var, dy, dx,
+  NPT_CHECK_CUDA(launch_pdl(kern, dim3(nblocks), dim3(kLnWarps * 32), smem, st, x, g, mean, var, dy, dyp, dx,
                             (__nv_bfloat16*)dxb, partial, rows, d, eps));
   NPT_LAUNCH_CHECK();
   return 0;
@@ -376,11 +393,11 @@ static int launch_bwd_k(const void* x, const float* g, const float* mean, const 
 
 template <int NV>
 static int launch_bwd(const void* x, const float* g, const float* mean, const float* var,
-                      const void* dy, bool in_bf16, float* dx, void* dxb, float* partial, bool dxsum, int nblocks,
+                      const void* dy, const void* dyp, bool in_bf16, float* dx, void* dxb, float* partial, bool dxsum, int nblocks,
                       int64_t rows, int d, float eps, cudaStream_t st) {
 #define NPT_LN_BWD(MODE)                                                                                        \
-  return dxsum ? launch_bwd_k<NV, MODE, true>(x, g, mean, var, dy, dx, dxb, partial, nblocks, rows, d, eps, st) \
-               : launch_bwd_k<NV, MODE, false>(x, g, mean, var, dy, dx, dxb, partial, nblocks, rows, d, eps, st)
+  return dxsum ? launch_bwd_k<NV, MODE, true>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st) \
+               : launch_bwd_k<NV, MODE, false>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st)
   if (in_bf16) { NPT_LN_BWD(2); }
   if (dxb) { NPT_LN_BWD(1); }  // bf16 throughput mode
   NPT_LN_BWD(0);
@@ -396,12 +413,13 @@ extern "C" {
 int npt_layernorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual,
                       float* y, void* y_bf16, float* mean, float* var, int64_t rows, int32_t d,
                       float eps, void* stream) {
-  return npt_layernorm_fwd_v2(x, 0, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, stream);
+  return npt_layernorm_fwd_v2(x, 0, nullptr, nullptr, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, stream);
 }
 
 int npt_layernorm_bf16_input_supported(int32_t d) { return (d % 4 == 0 && d <= kLnMaxVec * 128) ? 1 : 0; }
 
-int npt_layernorm_fwd_v2(const void* x, int32_t x_is_bf16, const float* gamma, const float* beta, const float* residual,
+int npt_layernorm_fwd_v2(const void* x, int32_t x_is_bf16, const void* x_peer, void* x_sum_bf16, const float* gamma,
+                         const float* beta, const float* residual,
                          float* y, void* y_bf16, float* mean, float* var, int64_t rows, int32_t d,
                          float eps, void* stream) {
   NPT_REQUIRE(rows >= 0 && d > 0, "layernorm_fwd: bad shape rows=%lld d=%d", (long long)rows, d);
@@ -410,17 +428,19 @@ int npt_layernorm_fwd_v2(const void* x, int32_t x_is_bf16, const float* gamma, c
   const bool vec = (d % 4 == 0) && d <= kLnMaxVec * 128 && (x_is_bf16 ? aligned8(x) : aligned16(x)) && aligned16(y) &&
                    aligned16(gamma) && aligned16(beta) && (!residual || aligned16(residual)) &&
                    (!y_bf16 || aligned8(y_bf16));
+  NPT_REQUIRE(!x_peer || (x_is_bf16 && aligned8(x_peer) && (!x_sum_bf16 || aligned8(x_sum_bf16))),
+              "layernorm_fwd: a peer partial needs bf16 inputs and 8-byte aligned buffers");
   NPT_REQUIRE(!x_is_bf16 || vec, "layernorm_fwd: a bf16 input needs d %% 4 == 0, d <= %d and aligned buffers", kLnMaxVec * 128);
   if (vec) {
     const int nv = (int)cdiv(d, 128);
     const bool ib = x_is_bf16 != 0;
     switch (nv) {
-      case 1: return launch_fwd<1>(x, ib, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      case 2: return launch_fwd<2>(x, ib, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      case 3: return launch_fwd<3>(x, ib, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      case 4: return launch_fwd<4>(x, ib, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      case 5: case 6: return launch_fwd<6>(x, ib, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      default: return launch_fwd<8>(x, ib, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 1: return launch_fwd<1>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 2: return launch_fwd<2>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 3: return launch_fwd<3>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 4: return launch_fwd<4>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 5: case 6: return launch_fwd<6>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      default: return launch_fwd<8>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
     }
   }
   NPT_CHECK_CUDA(launch_pdl(ln_fwd_block_kernel, dim3((unsigned)rows), dim3(256), 0, st, (const float*)x, gamma, beta, residual, y,
@@ -439,13 +459,13 @@ int npt_layernorm_bwd(const float* x, const float* gamma, const float* mean, con
                       const float* dy, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
                       int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
                       void* stream) {
-  return npt_layernorm_bwd_v2(x, dy, 0, gamma, mean, var, dx, dx_bf16, dgamma, dbeta, nullptr, rows, d, eps, workspace,
+  return npt_layernorm_bwd_v2(x, dy, 0, nullptr, gamma, mean, var, dx, dx_bf16, dgamma, dbeta, nullptr, rows, d, eps, workspace,
                               workspace_bytes, stream);
 }
 
 int npt_layernorm_bwd_colsum_supported(int32_t d) { return (d % 4 == 0 && d <= kLnMaxVec * 128) ? 1 : 0; }
 
-int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16, const float* gamma, const float* mean,
+int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16, const void* dy_peer, const float* gamma, const float* mean,
                          const float* var, float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum,
                          int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
                          void* stream) {
@@ -462,6 +482,7 @@ int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16,
                    (!dx || aligned16(dx)) && aligned16(gamma) && (!dx_bf16 || aligned8(dx_bf16)) &&
                    (size_t)kLnWarps * 3 * d * sizeof(float) <= 200 * 1024;
   const bool dxsum = dx_colsum != nullptr;
+  NPT_REQUIRE(!dy_peer || (ib && aligned8(dy_peer)), "layernorm_bwd: a peer partial needs bf16 inputs and an 8-byte aligned buffer");
   NPT_REQUIRE(!(dxsum || ib) || vec,
               "layernorm_bwd: fused dx column sums / bf16 inputs need d %% 4 == 0, d <= %d and aligned buffers", kLnMaxVec * 128);
   if (vec) {
@@ -469,12 +490,12 @@ int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16,
     const int nv = (int)cdiv(d, 128);
     int rc;
     switch (nv) {
-      case 1: rc = launch_bwd<1>(x, gamma, mean, var, dy, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      case 2: rc = launch_bwd<2>(x, gamma, mean, var, dy, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      case 3: rc = launch_bwd<3>(x, gamma, mean, var, dy, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      case 4: rc = launch_bwd<4>(x, gamma, mean, var, dy, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      case 5: case 6: rc = launch_bwd<6>(x, gamma, mean, var, dy, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      default: rc = launch_bwd<8>(x, gamma, mean, var, dy, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 1: rc = launch_bwd<1>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 2: rc = launch_bwd<2>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 3: rc = launch_bwd<3>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 4: rc = launch_bwd<4>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 5: case 6: rc = launch_bwd<6>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      default: rc = launch_bwd<8>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
     }
     if (rc) return rc;
   } else {

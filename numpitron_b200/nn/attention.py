@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from .. import distributed as npdist
+from ..distributed import peer
 from .. import ops
 from .. import runtime as rt
 from .activation import Softmax
@@ -62,12 +63,9 @@ class Attention(Model):
         if bf16 and ops.attention_supported(seq_len, dh):
             # fused tcgen05 attention: scores / probabilities never leave the SM
             att_b, lse = ops.attention_fwd(qkv, batch_size, seq_len, h, dh, divisor)
-            outputs = self.out_projection.forward(att_b, out=out)
             self.ctx |= {"qkv": qkv, "att": att_b, "lse": lse, "divisor": divisor,
                          "shape": (batch_size, seq_len, h, dh)}
-            if self.is_scattered and npdist.tensor_parallel_size() > 1:
-                npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
-            return outputs
+            return self._project_out(att_b, inputs.shape, out)
         nb = batch_size * h
         q_op = self._operand(qkv)
         head = (seq_len * ld, dh3)                                          # (batch, head) strides in qkv
@@ -86,10 +84,26 @@ class Attention(Model):
         ops.gemm(p_op, q_op, seq_len, dh, seq_len, lda=seq_len, ldb=ld, b_off=2 * dh, a_strides=mat,
                  b_strides=head, C_out=att, ldc=h * dh, c_strides=merged,
                  Cb_out=att_b, ldcb=h * dh, cb_strides=merged, batch=nb, batch_inner=h)
-        outputs = self.out_projection.forward(att_b if bf16 else att, out=out)
+        outputs = self.out_projection.forward(att_b if bf16 else att, out="bf16" if out == "peer" else out)
 
         self.ctx |= {"qkv": qkv, "attention_weights": attention_weights, "shape": (batch_size, seq_len, h, dh)}
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
+            npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
+        return outputs
+
+    def _project_out(self, att, out_shape, out: str):
+        """Output projection (row-parallel) + the tensor-parallel reduction of its result
+        (attention.py:57-58): an NCCL all-reduce, or — out == "peer" — no reduction here at all: the partial
+        goes to a peer-visible slot and the LayerNorm that follows adds the other rank's (distributed/peer.py)."""
+        tp = self.is_scattered and npdist.tensor_parallel_size() > 1
+        px = peer.exchange(out_shape) if (tp and out == "peer") else None
+        if px is not None:
+            slot, peer_ptr = px.slot("fwd", out_shape)
+            outputs = self.out_projection.forward(att, out="bf16", out_tensor=slot)
+            outputs._npt_peer = (px, peer_ptr)
+            return outputs
+        outputs = self.out_projection.forward(att, out="bf16" if out == "peer" else out)
+        if tp:
             npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
         return outputs
 
@@ -138,7 +152,18 @@ class Attention(Model):
     def _qkv_backward(self, d_qkv, out: str = "f32"):
         """QKV-projection backward; under TP the all-reduce of dX (attention.py:101-102) is started as
         soon as dX is enqueued and overlaps the dW GEMM."""
-        if self.is_scattered and npdist.tensor_parallel_size() > 1:
+        tp = self.is_scattered and npdist.tensor_parallel_size() > 1
+        if tp and out == "peer":
+            d_model = self.qkv_projection.weight.data.shape[0]
+            px = peer.exchange((*d_qkv.shape[:-1], d_model))
+            if px is not None:
+                slot, peer_ptr = px.slot("bwd", (*d_qkv.shape[:-1], d_model))
+                d_in = self.qkv_projection.backward(d_qkv, out="bf16", out_tensor=slot)
+                d_in._npt_peer = (px, peer_ptr)
+                return d_in
+        if out == "peer":
+            out = "bf16"
+        if tp:
             pending = []
             d_in = self.qkv_projection.backward(
                 d_qkv, out=out, on_dx=lambda dx: pending.append(npdist.all_reduce_async(dx, group=npdist.tensor_parallel_group())))

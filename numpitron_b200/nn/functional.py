@@ -60,7 +60,7 @@ def relu_bits_supported(d_out: int) -> bool:
     return rt.is_bf16() and d_out % 8 == 0
 
 
-def linear_forward(x, layer, wname="weight", bias=None, relu=False, out="f32", relu_bits=None):
+def linear_forward(x, layer, wname="weight", bias=None, relu=False, out="f32", relu_bits=None, out_tensor=None):
     """y = x @ W (+ b) (ReLU) — nn/linear.py:44-47.  x (..., d_in), W (d_in, d_out).
     `relu_bits`: optional int32 (ceil(d_out/32), T) buffer that receives the packed (y > 0) mask."""
     W = getattr(layer, wname).data
@@ -68,7 +68,7 @@ def linear_forward(x, layer, wname="weight", bias=None, relu=False, out="f32", r
     T = x.numel() // d_in
     A, lda = _act(x)
     B, ldb = _weight(layer, wname)
-    y, yb = _outputs((*x.shape[:-1], d_out), out)
+    y, yb = _outputs((*x.shape[:-1], d_out), out) if out_tensor is None else (None, out_tensor)  # bf16 peer slot
     ops.gemm(A, B, T, d_out, d_in, lda=lda, ldb=ldb, C_out=y, ldc=d_out, Cb_out=yb, ldcb=d_out, bias=bias, relu=relu,
              relu_bits_out=relu_bits)
     return _result(y, yb)
@@ -85,14 +85,14 @@ def linear_backward_weight(x, dy):
     return dW
 
 
-def linear_backward_input(dy, layer, wname="weight", mask=None, out="f32"):
+def linear_backward_input(dy, layer, wname="weight", mask=None, out="f32", out_tensor=None):
     """dx = dy @ W^T (optionally * (mask > 0): the fused ReLU.backward) — nn/linear.py:60."""
     W = getattr(layer, wname).data
     d_in, d_out = W.shape
     T = dy.numel() // d_out
     A, lda = _act(dy)
     B, ldb = _weight(layer, wname)
-    dx, dxb = _outputs((*dy.shape[:-1], d_in), out)
+    dx, dxb = _outputs((*dy.shape[:-1], d_in), out) if out_tensor is None else (None, out_tensor)  # bf16 peer slot
     mk, ldm, bits = None, 0, None
     if mask is not None:
         if mask.dtype == torch.int32:

@@ -5,6 +5,7 @@ from __future__ import annotations
 import torch
 
 from .. import distributed as npdist
+from ..distributed import peer
 from .. import runtime as rt
 from . import functional as F
 from .activation import ReLU
@@ -34,14 +35,33 @@ class MLP(Model):
             bits = rt.empty(((d_hidden + 31) // 32, inputs.numel() // inputs.shape[-1]), torch.int32)  # word-major
         hidden = self.column_linear.forward(inputs, relu=True, out="bf16", relu_bits=bits)
         self.ctx["relu_mask"] = bits if bits is not None else hidden
-        outputs = self.row_linear.forward(hidden, out=out)
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
+            px = peer.exchange(inputs.shape) if out == "peer" else None
+            if px is not None:
+                # no all-reduce: the partial goes to a peer-visible slot and the LayerNorm that follows adds
+                # the other rank's partial while it reads (distributed/peer.py)
+                slot, peer_ptr = px.slot("fwd", (*inputs.shape[:-1], self.row_linear.weight.data.shape[1]))
+                outputs = self.row_linear.forward(hidden, out="bf16", out_tensor=slot)
+                outputs._npt_peer = (px, peer_ptr)
+                return outputs
+            outputs = self.row_linear.forward(hidden, out="bf16" if out == "peer" else out)
             npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
-        return outputs
+            return outputs
+        return self.row_linear.forward(hidden, out="bf16" if out == "peer" else out)
 
     def backward(self, d_out, out: str = "f32"):
         d_out = self.row_linear.backward(d_out, mask=self.ctx.pop("relu_mask"), out="bf16")  # (dy@W2^T) * (a>0)
+        if out == "peer" and not (self.is_scattered and npdist.tensor_parallel_size() > 1):
+            out = "bf16"
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
+            px = peer.exchange(d_out.shape) if out == "peer" else None
+            if px is not None:
+                slot, peer_ptr = px.slot("bwd", (*d_out.shape[:-1], self.column_linear.weight.data.shape[0]))
+                d_in = self.column_linear.backward(d_out, out="bf16", out_tensor=slot)
+                d_in._npt_peer = (px, peer_ptr)
+                return d_in
+            if out == "peer":
+                out = "bf16"
             # all-reduce of dX (mlp.py:52-53) overlapped with the column-linear dW / db kernels
             pending = []
             d_out = self.column_linear.backward(

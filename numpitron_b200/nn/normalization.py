@@ -18,8 +18,17 @@ class LayerNorm(Layer):
     def forward(self, inputs, residual=None):
         """gamma*(x-mean)/sqrt(var+eps)+beta, optionally + residual in the same pass
         (TransformerBlock's `norm(sub(x)) + x`, transformer_block.py:20-21)."""
-        outputs, mean, var = ops.layernorm_fwd(inputs, self.weight.data, self.bias.data, self.eps,
-                                               residual=residual, want_bf16=rt.is_bf16())
+        pinfo = getattr(inputs, "_npt_peer", None)
+        if pinfo is not None:
+            # tensor parallelism over 2 ranks: `inputs` is this rank's partial, the other rank's is read from
+            # peer memory inside the kernel (no all-reduce kernel; distributed/peer.py)
+            px, peer_ptr = pinfo
+            px.barrier()
+            outputs, mean, var, inputs = ops.layernorm_fwd(inputs, self.weight.data, self.bias.data, self.eps,
+                                                           residual=residual, want_bf16=rt.is_bf16(), x_peer=peer_ptr)
+        else:
+            outputs, mean, var = ops.layernorm_fwd(inputs, self.weight.data, self.bias.data, self.eps,
+                                                   residual=residual, want_bf16=rt.is_bf16())
         self.ctx |= {"inputs": inputs, "mean": mean, "var": var}
         return outputs
 
@@ -28,9 +37,14 @@ class LayerNorm(Layer):
         it as a bf16 tensor alone, and that layer's bias gradient (the column sums of d_in) is computed
         here, in the pass that produces d_in."""
         inputs, mean, var = self.ctx.pop("inputs"), self.ctx.pop("mean"), self.ctx.pop("var")
+        pinfo = getattr(d_out, "_npt_peer", None)
+        peer_ptr = 0
+        if pinfo is not None:  # d_out is this rank's partial dX; the other rank's is added inside the kernel
+            pinfo[0].barrier()
+            peer_ptr = pinfo[1]
         d_in, d_weight, d_bias = ops.layernorm_bwd(inputs, self.weight.data, mean, var, d_out, self.eps,
                                                    want_bf16=rt.is_bf16(), bf16_only=gemm_only and rt.is_bf16(),
-                                                   want_colsum=gemm_only)
+                                                   want_colsum=gemm_only, dy_peer=peer_ptr)
         self.update_parameter("weight", gradient=d_weight)
         self.update_parameter("bias", gradient=d_bias)
         return d_in

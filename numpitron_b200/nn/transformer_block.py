@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 from .. import ops
+from ..distributed import peer
 from .. import runtime as rt
 from .attention import Attention
 from .mlp import MLP
@@ -26,7 +27,10 @@ class TransformerBlock(Model):
         """bf16 mode: the sub-layer outputs LayerNorm normalises, and the dX that reaches a LayerNorm's
         backward, leave their GEMM as bf16 alone (the residual stream itself stays fp32): half the bytes to
         store, to all-reduce across tensor-parallel ranks and for LayerNorm to read."""
-        return "bf16" if rt.is_bf16() and ops.layernorm_bf16_input_supported(self.d_model) else "f32"
+        if not (rt.is_bf16() and ops.layernorm_bf16_input_supported(self.d_model)):
+            return "f32"
+        # tp = 2: the partial results are exchanged through peer memory and reduced inside LayerNorm
+        return "peer" if peer.enabled() else "bf16"
 
     def forward(self, inputs):
         # LayerNorm is applied to the SUB-LAYER OUTPUT, then the residual is added (Q1); the add is

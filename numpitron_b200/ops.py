@@ -102,22 +102,28 @@ def layernorm_bf16_input_supported(d: int) -> bool:
     return bool(_lib_().npt_layernorm_bf16_input_supported(int(d)))
 
 
-def layernorm_fwd(x, gamma, beta, eps, residual=None, want_bf16=False):
-    """x: fp32, or bf16 (a sub-layer output that came out of its GEMM epilogue as bf16 alone)."""
+def layernorm_fwd(x, gamma, beta, eps, residual=None, want_bf16=False, x_peer: int = 0):
+    """x: fp32, or bf16 (a sub-layer output that came out of its GEMM epilogue as bf16 alone).
+    `x_peer`: device pointer of the other tensor-parallel rank's partial of x (peer memory); the kernel
+    then normalises round_bf16(x + x_peer) and the reduced input is returned as a 4th value."""
     lib = _lib_()
     d = x.shape[-1]
     rows = x.numel() // d
     y = rt.empty(x.shape)
     yb = rt.empty(x.shape, _BF16) if want_bf16 else None
     mean, var = rt.empty((rows,)), rt.empty((rows,))
-    check(lib.npt_layernorm_fwd_v2(_p(x), int(x.dtype == _BF16), _p(gamma), _p(beta), _p(residual), _p(y), _p(yb),
-                                   _p(mean), _p(var), rows, d, eps, rt.stream()), "npt_layernorm_fwd_v2")
+    x_sum = rt.empty(x.shape, _BF16) if x_peer else None
+    check(lib.npt_layernorm_fwd_v2(_p(x), int(x.dtype == _BF16), x_peer or None, _p(x_sum), _p(gamma), _p(beta),
+                                   _p(residual), _p(y), _p(yb), _p(mean), _p(var), rows, d, eps, rt.stream()),
+          "npt_layernorm_fwd_v2")
     if yb is not None:
         rt.attach_bf16(y, yb)
+    if x_peer:
+        return y, mean, var, x_sum
     return y, mean, var
 
 
-def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False, bf16_only=False, want_colsum=False):
+def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False, bf16_only=False, want_colsum=False, dy_peer: int = 0):
     """Returns (dx, dgamma, dbeta); with bf16_only dx is a bf16 tensor (it only feeds GEMMs).
     `want_colsum`: the column sums of dx (the bias gradient of the Linear in front of this LayerNorm) are
     computed in the same pass and attached to the returned dx as `_npt_colsum` (nn.functional.bias_grad
@@ -137,7 +143,8 @@ def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False, bf16_only=False
         x = cast_bf16(x)
     if in_bf16 and dy.dtype != _BF16:
         dy = cast_bf16(dy)
-    check(lib.npt_layernorm_bwd_v2(_p(x), _p(dy), int(in_bf16), _p(gamma), _p(mean), _p(var), _p(dx), _p(dxb),
+    assert not dy_peer or in_bf16
+    check(lib.npt_layernorm_bwd_v2(_p(x), _p(dy), int(in_bf16), dy_peer or None, _p(gamma), _p(mean), _p(var), _p(dx), _p(dxb),
                                    _p(dgamma), _p(dbeta), _p(colsum_out), rows, d, eps, ws.data_ptr(), ws.numel(),
                                    rt.stream()), "npt_layernorm_bwd_v2")
     out = dxb if bf16_only else dx
