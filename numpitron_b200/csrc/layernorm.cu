@@ -15,7 +15,8 @@ constexpr int kLnMaxVec = 8;     // float4 per lane -> d <= 1024 on the register
 // EXACT: every operation rounded separately like NumPy (IEEE division per element) — the fp32 parity
 // mode.  !EXACT (a bf16 output is requested, i.e. the bf16 throughput mode): one reciprocal per row and a
 // multiply per element; the IEEE divisions were ~40 % of the instructions these kernels issue.
-// MODE 0 = EXACT (fp32 input), 1 = fast (fp32 input), 2 = fast, bf16 input (x — and dy in the backward — come
+// MODE 0 = EXACT (fp32 input), 1 = fast (fp32 input), 2 = fast, bf16 input, 3 = 2 + the other tensor-parallel
+// rank's partial is added while reading (x — and dy in the backward — come
 // from a GEMM epilogue as bf16 alone: half the bytes to write there, to all-reduce under tensor
 // parallelism and to read here).
 __device__ __forceinline__ float4 ld_bf16x4_stream(const void* p) {
@@ -34,10 +35,12 @@ __device__ __forceinline__ float4 ln_load4(const void* base, int64_t row, int d,
 // tensor (a peer-memory pointer over NVLink).  The sum is rounded to bf16 — exactly what a bf16
 // all-reduce would have left in memory — so both ranks, and the forward and backward passes, see
 // identical values.
-template <bool INBF>
+// PEER is a template parameter (MODE 3), not a run-time test on the pointer: with the test the
+// compiler serialised the loads of a row behind it and every LayerNorm launch got 3-4 us slower.
+template <bool INBF, bool PEER>
 __device__ __forceinline__ float4 ln_load4_sum(const void* base, const void* peer, int64_t row, int d, int c) {
   float4 a = ln_load4<INBF>(base, row, d, c);
-  if (INBF && peer) {
+  if (INBF && PEER) {
     const float4 b = ln_load4<INBF>(peer, row, d, c);
     a.x = __bfloat162float(__float2bfloat16_rn(a.x + b.x)); a.y = __bfloat162float(__float2bfloat16_rn(a.y + b.y));
     a.z = __bfloat162float(__float2bfloat16_rn(a.z + b.z)); a.w = __bfloat162float(__float2bfloat16_rn(a.w + b.w));
@@ -58,7 +61,7 @@ ln_fwd_warp_kernel(const void* __restrict__ x, const void* __restrict__ x_peer, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.x * kLnWarps + warp;
   if (row >= rows) return;
-  constexpr bool EXACT = MODE == 0, INBF = MODE == 2;
+  constexpr bool EXACT = MODE == 0, INBF = MODE >= 2, PEER = MODE == 3;
   const int nvec = d >> 2;  // float4 per row
   float4 v[NV];
   float s = 0.f;
@@ -66,11 +69,17 @@ ln_fwd_warp_kernel(const void* __restrict__ x, const void* __restrict__ x_peer, 
   for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nvec) {
-      v[i] = ln_load4_sum<INBF>(x, x_peer, row, d, c);
-      if (INBF && x_sum) st_bf16x4(x_sum + row * d + (int64_t)c * 4, v[i]);  // the reduced input, kept for the backward
+      v[i] = ln_load4_sum<INBF, PEER>(x, x_peer, row, d, c);
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (PEER && x_sum) {  // the reduced input, kept for the backward (after the loads: nothing between them)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) st_bf16x4(x_sum + row * d + (int64_t)c * 4, v[i]);
     }
   }
   const float mean = warp_sum(s) / (float)d;
@@ -173,7 +182,7 @@ ln_bwd_warp_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
   pdl_trigger();
   extern __shared__ float sm[];  // [kLnWarps][NSL][d]
   constexpr int NSL = DXSUM ? 3 : 2;
-  constexpr bool EXACT = MODE == 0, INBF = MODE == 2;
+  constexpr bool EXACT = MODE == 0, INBF = MODE >= 2, PEER = MODE == 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = d >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
@@ -207,7 +216,7 @@ ln_bwd_warp_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const int c = lane + i * 32;
-          if (c < nvec) { xv[u][i] = ln_load4<INBF>(x, row, d, c); dv[u][i] = ln_load4_sum<INBF>(dy, dy_peer, row, d, c); }
+          if (c < nvec) { xv[u][i] = ln_load4<INBF>(x, row, d, c); dv[u][i] = ln_load4_sum<INBF, PEER>(dy, dy_peer, row, d, c); }
         }
         mean[u] = mean_in[row];
         const float var = var_in[row];
@@ -366,7 +375,10 @@ static int launch_fwd(const void* x, bool in_bf16, const void* xp, void* xs, con
                       void* yb, float* mean, float* var, int64_t rows, int d, float eps,
                       cudaStream_t st) {
   const int64_t grid = cdiv(rows, kLnWarps);
-  if (in_bf16)
+  if (in_bf16 && xp)
+    NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, 3>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
+        x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
+  else if (in_bf16)
     NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, 2>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
         x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
   else if (yb)  // bf16 throughput mode
@@ -398,6 +410,7 @@ static int launch_bwd(const void* x, const float* g, const float* mean, const fl
 #define NPT_LN_BWD(MODE)                                                                                        \
   return dxsum ? launch_bwd_k<NV, MODE, true>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st) \
                : launch_bwd_k<NV, MODE, false>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st)
+  if (in_bf16 && dyp) { NPT_LN_BWD(3); }
   if (in_bf16) { NPT_LN_BWD(2); }
   if (dxb) { NPT_LN_BWD(1); }  // bf16 throughput mode
   NPT_LN_BWD(0);

@@ -55,14 +55,16 @@ def main(tp, dp, precision):
         opt.step()
         close(loss, W[f"rank{rank}/loss{i}"], rtol, f"loss{i}")
     close(model.input_embedding.embedding.data, W[f"rank{rank}/E_final"], rtol, "E_final")
-    # Adam's update is lr*g/(|g|+eps): with bf16 operands a noisy tiny gradient moves a weight by up
-    # to lr per step, so after 3 steps weights are compared to within 3.5*lr absolute in bf16 mode.
+    # Adam's update is lr*m/(sqrt(v)+eps) ~ lr*sign(g) in the first steps: with bf16 operands a tiny
+    # gradient whose sign flips moves that weight by up to 2*lr per step the other way, so after 3 steps
+    # single weights may sit up to 6*lr from the reference; on average they must agree far better.
     w_got = to_numpy(model.block_0.mlp.column_linear.weight.data)
     w_want = W[f"rank{rank}/w1_final_block0"]
     if precision == "fp32":
         close(w_got, w_want, rtol, "w1_final")
     else:
-        assert np.abs(w_got - w_want).max() <= 3.5e-4, np.abs(w_got - w_want).max()
+        diff = np.abs(w_got - w_want)
+        assert diff.max() <= 6.1e-4 and diff.mean() <= 5e-5, (diff.max(), diff.mean())
 
     # the CUDA-graph replay (NCCL all-reduces captured inside) gives the eager numbers
     model2 = Transformer(**TINY, rng=np.random.default_rng(42))
