@@ -83,6 +83,12 @@ typedef struct npt_gemm_args {
    * relu_bits_out: written by a relu=1 GEMM (bit = output > 0); mask_bits: consumed like `mask`
    * by the backward GEMM — 1/16 of the bytes of a bf16 mask and no extra pass in the epilogue. */
   uint32_t* relu_bits_out; const uint32_t* mask_bits; int64_t ld_bits;
+  /* Optional second destination of the bf16 output (same ldcb / strides as C_bf16; bf16 tensor-core mode,
+   * single-output launches): every tile is also TMA-stored there.  Under tensor parallelism this is a buffer
+   * in the OTHER rank's memory (NVLink P2P), so the partial result of a row-parallel layer (nn/attention.py:56,
+   * nn/mlp.py:34) lands next to the peer's own partial while the GEMM is still running, and the LayerNorm
+   * that follows adds the two from local memory (npt_layernorm_fwd_v2, x_peer). */
+  void* C_bf16_peer;
 } npt_gemm_args;
 
 size_t npt_gemm_workspace_bytes(const npt_gemm_args* args);

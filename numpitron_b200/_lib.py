@@ -36,6 +36,7 @@ class GemmArgs(C.Structure):
         ("ldmask", c_int64), ("stride_mask_outer", c_int64), ("stride_mask_inner", c_int64),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("relu_bits_out", c_void_p), ("mask_bits", c_void_p), ("ld_bits", c_int64),
+        ("C_bf16_peer", c_void_p),
     ]
 
 

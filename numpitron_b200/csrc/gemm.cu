@@ -137,6 +137,8 @@ int npt_gemm(const npt_gemm_args* args, void* stream) {
   }
   const GemmEpilogue epi = make_epilogue(a);
   const int splits = choose_splits(a);
+  NPT_REQUIRE(!a.C_bf16_peer || (a.mode == NPT_GEMM_BF16_TC && splits == 1),
+              "gemm: C_bf16_peer needs the bf16 tensor-core mode and a launch without split-K");
   float* partial = nullptr;
   if (splits > 1) {
     const size_t need = (size_t)splits * a.batch * (size_t)a.M * a.N * sizeof(float);

@@ -169,8 +169,8 @@ extern "C" int npt_debug_gemm_trace(long long* host_out) {  // 256 x 64 stamps o
 
 #define NPT_TC_EXTERN(BNV)                                                                                  \
   extern template int launch_tc_bn<BNV>(const TcParams&, const GemmEpilogue&, float*, const CUtensorMap&,      \
-                                        const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, bool, bool, \
-                                        int, int, cudaStream_t);
+                                        const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, bool, \
+                                        bool, int, int, cudaStream_t);
 NPT_TC_EXTERN(64) NPT_TC_EXTERN(128) NPT_TC_EXTERN(192) NPT_TC_EXTERN(256)
 #undef NPT_TC_EXTERN
 
@@ -179,9 +179,10 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
   if (splits == 1) cfg = tc_config(a);
   const int bn = cfg.bn, cl = cfg.cl;
   const int64_t n_bi = a.batch_inner, n_bo = cdiv(a.batch, a.batch_inner);
-  CUtensorMap tmA, tmB, tmC, tmCb;
+  CUtensorMap tmA, tmB, tmC, tmCb, tmP;
   memset(&tmC, 0, sizeof(tmC));
   memset(&tmCb, 0, sizeof(tmCb));
+  memset(&tmP, 0, sizeof(tmP));
   int rc;
   if (a.trans_a) rc = make_map_bf16(&tmA, a.A, a.M, a.K, a.lda, n_bi, a.stride_a_inner, n_bo, a.stride_a_outer, 64, 64);
   else           rc = make_map_bf16(&tmA, a.A, a.K, a.M, a.lda, n_bi, a.stride_a_inner, n_bo, a.stride_a_outer, 64, TC_BM);
@@ -201,6 +202,7 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
   NPT_REQUIRE(total < ((int64_t)1 << 31), "gemm(tc): too many tiles");
   p.total_tiles = (int)total;
   p.raw = splits > 1;
+  p.peer_store = 0;
 #ifdef NPT_GEMM_DEBUG
   {
     const char* d = getenv("NUMPITRON_GEMM_DBG");
@@ -250,12 +252,20 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
       if (rc) return rc;
     }
   }
+  if (a.C_bf16_peer) {  // second (peer-GPU) destination of the bf16 output: fast epilogue only
+    NPT_REQUIRE(!p.raw && kind != EPI_GENERAL && a.C_bf16 && !a.C && aligned16(a.C_bf16_peer),
+                "gemm(tc): C_bf16_peer needs a single bf16 output that TMA can store, no split-K, 16-byte aligned buffers");
+    rc = make_map(&tmP, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_128B, a.C_bf16_peer, a.N, a.M, a.ldcb, n_bi,
+                  a.stride_cb_inner, n_bo, a.stride_cb_outer, 64, 32);
+    if (rc) return rc;
+    p.peer_store = 1;
+  }
   NPT_REQUIRE(cl == 1 || kind != EPI_GENERAL, "gemm(tc): internal error, CTA pairs need the fast epilogue");
   const bool a_mn = a.trans_a != 0, b_mn = a.trans_b == 0;
-  if (bn == 64) return launch_tc_bn<64>(p, epi, partial, tmA, tmB, tmC, tmCb, a_mn, b_mn, cl, kind, st);
-  if (bn == 192) return launch_tc_bn<192>(p, epi, partial, tmA, tmB, tmC, tmCb, a_mn, b_mn, cl, kind, st);
-  if (bn == 256) return launch_tc_bn<256>(p, epi, partial, tmA, tmB, tmC, tmCb, a_mn, b_mn, cl, kind, st);
-  return launch_tc_bn<128>(p, epi, partial, tmA, tmB, tmC, tmCb, a_mn, b_mn, cl, kind, st);
+  if (bn == 64) return launch_tc_bn<64>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, a_mn, b_mn, cl, kind, st);
+  if (bn == 192) return launch_tc_bn<192>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, a_mn, b_mn, cl, kind, st);
+  if (bn == 256) return launch_tc_bn<256>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, a_mn, b_mn, cl, kind, st);
+  return launch_tc_bn<128>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, a_mn, b_mn, cl, kind, st);
 }
 
 }  // namespace npt

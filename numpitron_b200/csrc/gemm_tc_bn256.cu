@@ -4,5 +4,5 @@
 
 namespace npt {
 template int launch_tc_bn<256>(const TcParams&, const GemmEpilogue&, float*, const CUtensorMap&, const CUtensorMap&,
-                               const CUtensorMap&, const CUtensorMap&, bool, bool, int, int, cudaStream_t);
+                               const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, bool, bool, int, int, cudaStream_t);
 }  // namespace npt

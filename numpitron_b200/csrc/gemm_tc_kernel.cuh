@@ -242,6 +242,7 @@ struct TcParams {
   int m_tiles, n_tiles, total_tiles;
   int tma_store;  // 1: staged TMA-store epilogue; 0: direct register stores (unaligned outputs)
   int raw;        // 1: split-K partial (no epilogue math), stored through map C as {N, M, batch, split}
+  int peer_store; // 1: the bf16 output is also stored through map P (a peer GPU's buffer)
 #ifdef NPT_GEMM_DEBUG
   int dbg;        // timing experiments only: 1 = no epilogue stores, 2 = no MMA issue, 4 = no TMA loads
   long long* trace;  // [cta][64] clock64() stamps (slot 0/1: entry / after prologue, then 7 per tile)
@@ -284,7 +285,8 @@ template <int BN, bool A_MN, bool B_MN, int CL, int EPI>
 __global__ void __launch_bounds__(EPI == EPI_GENERAL ? TC_THREADS : TC_THREADS_FAST, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCb,
-               const TcParams p, const GemmEpilogue epi, float* __restrict__ partial) {
+               const __grid_constant__ CUtensorMap tmP, const TcParams p, const GemmEpilogue epi,
+               float* __restrict__ partial) {
   static_assert(CL == 1 || EPI != EPI_GENERAL, "CTA pairs run the fast epilogue only");
   using L = TcSmem<BN, CL>;
   constexpr int TC_STAGES = L::STAGES;
@@ -306,6 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.tma_store) {
       if (epi.C || p.raw) tma_prefetch_desc(&tmC);
       if (epi.Cb && !p.raw) tma_prefetch_desc(&tmCb);
+      if (p.peer_store) tma_prefetch_desc(&tmP);
     }
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full_bar + s, 1);
@@ -584,6 +587,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) {
             tma_store_4d(out_map, stage_base + (store_i & 1) * L::FAST_SLOT_BYTES, out_bf16 ? nb - 32 : nb, mrow0, c2, c3);
+            // tensor parallelism: the same staged tile also goes to the peer GPU (posted NVLink writes)
+            if (p.peer_store) tma_store_4d(&tmP, stage_base + (store_i & 1) * L::FAST_SLOT_BYTES, nb - 32, mrow0, c2, c3);
             tma_store_commit();
           }
           ++store_i;
@@ -822,7 +827,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 template <int BN, bool A_MN, bool B_MN, int CL, int EPI>
 static int launch_tc_cl(const TcParams& p, const GemmEpilogue& epi, float* partial, const CUtensorMap& tmA,
-                        const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCb, cudaStream_t st) {
+                        const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCb, const CUtensorMap& tmP, cudaStream_t st) {
   using L = TcSmem<BN, CL>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL, EPI>;
   constexpr int threads = EPI == EPI_GENERAL ? TC_THREADS : TC_THREADS_FAST;
@@ -835,7 +840,7 @@ static int launch_tc_cl(const TcParams& p, const GemmEpilogue& epi, float* parti
   if (grid < 1) grid = 1;
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (CL == 1) {
-    NPT_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(threads), L::TOTAL, st, tmA, tmB, tmC, tmCb, p, epi, partial));
+    NPT_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(threads), L::TOTAL, st, tmA, tmB, tmC, tmCb, tmP, p, epi, partial));
   } else {
     grid -= grid % CL;
     cudaLaunchConfig_t cfg = {};
@@ -852,7 +857,7 @@ static int launch_tc_cl(const TcParams& p, const GemmEpilogue& epi, float* parti
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    NPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmCb, p, epi, partial));
+    NPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmCb, tmP, p, epi, partial));
   }
   NPT_LAUNCH_CHECK();
   return 0;
@@ -873,32 +878,33 @@ inline int tc_epi_kind(int flags) {
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const TcParams& p, const GemmEpilogue& epi, float* partial, const CUtensorMap& tmA,
-                     const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCb, int cl, int kind,
-                     cudaStream_t st) {
-  if (kind == EPI_GENERAL) return launch_tc_cl<BN, A_MN, B_MN, 1, EPI_GENERAL>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
+                     const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCb, const CUtensorMap& tmP, int cl,
+                     int kind, cudaStream_t st) {
+  if (kind == EPI_GENERAL) return launch_tc_cl<BN, A_MN, B_MN, 1, EPI_GENERAL>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, st);
   if constexpr (BN >= 128 && !(BN == 192 && B_MN)) {  // CTA pairs (cta_group::2)
     if (cl == 2) {
-#define NPT_X(K) if (kind == (K)) return launch_tc_cl<BN, A_MN, B_MN, 2, (K)>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
+#define NPT_X(K) if (kind == (K)) return launch_tc_cl<BN, A_MN, B_MN, 2, (K)>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, st);
       NPT_TC_FAST_KINDS(NPT_X)
 #undef NPT_X
-      return launch_tc_cl<BN, A_MN, B_MN, 2, EPI_DYNAMIC>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
+      return launch_tc_cl<BN, A_MN, B_MN, 2, EPI_DYNAMIC>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, st);
     }
   }
   NPT_REQUIRE(cl == 1, "gemm(tc): no CTA-pair kernel for this tile shape");
-#define NPT_X(K) if (kind == (K)) return launch_tc_cl<BN, A_MN, B_MN, 1, (K)>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
+#define NPT_X(K) if (kind == (K)) return launch_tc_cl<BN, A_MN, B_MN, 1, (K)>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, st);
   NPT_TC_FAST_KINDS(NPT_X)
 #undef NPT_X
-  return launch_tc_cl<BN, A_MN, B_MN, 1, EPI_DYNAMIC>(p, epi, partial, tmA, tmB, tmC, tmCb, st);
+  return launch_tc_cl<BN, A_MN, B_MN, 1, EPI_DYNAMIC>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, st);
 }
 
 // One tile width per translation unit (gemm_tc_bn*.cu instantiate this).
 template <int BN>
 int launch_tc_bn(const TcParams& p, const GemmEpilogue& epi, float* partial, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                 const CUtensorMap& tmC, const CUtensorMap& tmCb, bool a_mn, bool b_mn, int cl, int kind, cudaStream_t st) {
-  if (a_mn && b_mn) return launch_tc<BN, true, true>(p, epi, partial, tmA, tmB, tmC, tmCb, cl, kind, st);
-  if (a_mn && !b_mn) return launch_tc<BN, true, false>(p, epi, partial, tmA, tmB, tmC, tmCb, cl, kind, st);
-  if (!a_mn && b_mn) return launch_tc<BN, false, true>(p, epi, partial, tmA, tmB, tmC, tmCb, cl, kind, st);
-  return launch_tc<BN, false, false>(p, epi, partial, tmA, tmB, tmC, tmCb, cl, kind, st);
+                 const CUtensorMap& tmC, const CUtensorMap& tmCb, const CUtensorMap& tmP, bool a_mn, bool b_mn, int cl, int kind,
+                 cudaStream_t st) {
+  if (a_mn && b_mn) return launch_tc<BN, true, true>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, cl, kind, st);
+  if (a_mn && !b_mn) return launch_tc<BN, true, false>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, cl, kind, st);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, cl, kind, st);
+  return launch_tc<BN, false, false>(p, epi, partial, tmA, tmB, tmC, tmCb, tmP, cl, kind, st);
 }
 
 }  // namespace npt

@@ -3,16 +3,20 @@
 The reference all-reduces the output of every row-parallel layer (forward: nn/attention.py:57-58,
 nn/mlp.py:35-36) and the dX of every column-parallel layer (backward: attention.py:101-102,
 mlp.py:52-53); in a TransformerBlock each of those tensors is consumed by exactly one kernel, the
-LayerNorm forward / backward that follows.  With tp = 2 on one NVLink box the all-reduce kernel can be
-dropped: each rank writes its partial into a buffer the other rank can address (symmetric memory,
-NVLink P2P), the two ranks meet at a device-side barrier, and the LayerNorm kernel reads
-`round_bf16(mine + peer's)` directly (`npt_layernorm_*_v2`, x_peer / dy_peer).  That replaces a 71 us
-NCCL all-reduce of 25 MiB (measured, 369 GB/s) plus LayerNorm's re-read of the result by one P2P read
-inside a kernel that runs anyway.
+LayerNorm forward / backward that follows.  With tp = 2 on one NVLink box the all-reduce kernel is
+dropped: the GEMM epilogue TMA-stores every tile of its partial twice — into its own buffer and into
+a buffer in the OTHER rank's memory (symmetric memory, NVLink P2P; `npt_gemm_args.C_bf16_peer`), so the
+exchange rides on posted NVLink writes while the GEMM is still computing.  The two ranks then meet at
+a device-side barrier and the LayerNorm kernel reads `round_bf16(mine + peer's)` from local memory
+(`npt_layernorm_*_v2`, x_peer / dy_peer).  That replaces a 71 us NCCL all-reduce of 25 MiB (measured,
+369 GB/s) plus LayerNorm's re-read of the result.  (A first version let LayerNorm *read* the peer's
+buffer over NVLink: P2P loads are latency-bound, the kernel got several times slower and most of the
+gain was lost.)
 
-Slots: two per direction, used alternately.  Rank A reads B's slot s after barrier i; B overwrites s
-two exchanges later, after barrier i+1, which A only reaches once its read (earlier in A's stream)
-has been issued and completed — so one barrier per exchange suffices.
+Slots: per direction two "own" and two "receive" slots, used alternately.  Rank A's GEMM writes B's
+receive slot s for exchange i; B reads it after barrier i and A writes it again two exchanges later,
+after barrier i+1, which B only reaches once that read (earlier in B's stream) is done — so one
+barrier per exchange suffices.
 
 NUMPITRON_TP_PEER=0 disables this and keeps the NCCL all-reduces.
 """
@@ -32,7 +36,7 @@ class PeerExchange:
         import torch.distributed._symmetric_memory as symm
 
         self.slot_bytes = (slot_bytes + 255) // 256 * 256
-        self.buf = symm.empty(4 * self.slot_bytes, dtype=torch.uint8, device=rt.device())
+        self.buf = symm.empty(8 * self.slot_bytes, dtype=torch.uint8, device=rt.device())
         self.hdl = symm.rendezvous(self.buf, pg)
         assert self.hdl.world_size == 2
         self.rank = self.hdl.rank
@@ -40,17 +44,19 @@ class PeerExchange:
         self.counters = {"fwd": 0, "bwd": 0}
 
     def slot(self, direction: str, shape, dtype=torch.bfloat16):
-        """(local tensor viewing the next slot of `direction`, the peer's pointer to ITS copy of that slot)."""
-        i = (0 if direction == "fwd" else 2) + (self.counters[direction] & 1)
+        """Next exchange of `direction`: (own: local tensor the GEMM writes its partial to,
+        send_ptr: address in the PEER's memory where the same partial must also be stored,
+        recv_ptr: address in LOCAL memory where the peer stores its partial)."""
+        i = (0 if direction == "fwd" else 4) + (self.counters[direction] & 1)
         self.counters[direction] += 1
         n = 1
         for s in shape:
             n *= int(s)
         nbytes = n * torch.empty((), dtype=dtype).element_size()
         assert nbytes <= self.slot_bytes, "peer slot too small"
-        off = i * self.slot_bytes
-        t = self.buf[off:off + nbytes].view(dtype).view(*shape)
-        return t, self.peer_base + off
+        own_off, recv_off = i * self.slot_bytes, (i + 2) * self.slot_bytes
+        own = self.buf[own_off:own_off + nbytes].view(dtype).view(*shape)
+        return own, self.peer_base + recv_off, self.buf.data_ptr() + recv_off
 
     def barrier(self):
         """Device-side barrier of the two ranks on the current stream: both partials are complete."""

@@ -98,9 +98,9 @@ class Attention(Model):
         tp = self.is_scattered and npdist.tensor_parallel_size() > 1
         px = peer.exchange(out_shape) if (tp and out == "peer") else None
         if px is not None:
-            slot, peer_ptr = px.slot("fwd", out_shape)
-            outputs = self.out_projection.forward(att, out="bf16", out_tensor=slot)
-            outputs._npt_peer = (px, peer_ptr)
+            slot, send_ptr, recv_ptr = px.slot("fwd", out_shape)
+            outputs = self.out_projection.forward(att, out="bf16", out_tensor=slot, peer_out=send_ptr)
+            outputs._npt_peer = (px, recv_ptr)
             return outputs
         outputs = self.out_projection.forward(att, out="bf16" if out == "peer" else out)
         if tp:
@@ -157,9 +157,9 @@ class Attention(Model):
             d_model = self.qkv_projection.weight.data.shape[0]
             px = peer.exchange((*d_qkv.shape[:-1], d_model))
             if px is not None:
-                slot, peer_ptr = px.slot("bwd", (*d_qkv.shape[:-1], d_model))
-                d_in = self.qkv_projection.backward(d_qkv, out="bf16", out_tensor=slot)
-                d_in._npt_peer = (px, peer_ptr)
+                slot, send_ptr, recv_ptr = px.slot("bwd", (*d_qkv.shape[:-1], d_model))
+                d_in = self.qkv_projection.backward(d_qkv, out="bf16", out_tensor=slot, peer_out=send_ptr)
+                d_in._npt_peer = (px, recv_ptr)
                 return d_in
         if out == "peer":
             out = "bf16"

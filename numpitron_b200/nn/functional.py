@@ -60,7 +60,8 @@ def relu_bits_supported(d_out: int) -> bool:
     return rt.is_bf16() and d_out % 8 == 0
 
 
-def linear_forward(x, layer, wname="weight", bias=None, relu=False, out="f32", relu_bits=None, out_tensor=None):
+def linear_forward(x, layer, wname="weight", bias=None, relu=False, out="f32", relu_bits=None, out_tensor=None,
+                   peer_out: int = 0):
     """y = x @ W (+ b) (ReLU) — nn/linear.py:44-47.  x (..., d_in), W (d_in, d_out).
     `relu_bits`: optional int32 (ceil(d_out/32), T) buffer that receives the packed (y > 0) mask."""
     W = getattr(layer, wname).data
@@ -70,7 +71,7 @@ def linear_forward(x, layer, wname="weight", bias=None, relu=False, out="f32", r
     B, ldb = _weight(layer, wname)
     y, yb = _outputs((*x.shape[:-1], d_out), out) if out_tensor is None else (None, out_tensor)  # bf16 peer slot
     ops.gemm(A, B, T, d_out, d_in, lda=lda, ldb=ldb, C_out=y, ldc=d_out, Cb_out=yb, ldcb=d_out, bias=bias, relu=relu,
-             relu_bits_out=relu_bits)
+             relu_bits_out=relu_bits, Cb_peer=peer_out)
     return _result(y, yb)
 
 
@@ -85,7 +86,7 @@ def linear_backward_weight(x, dy):
     return dW
 
 
-def linear_backward_input(dy, layer, wname="weight", mask=None, out="f32", out_tensor=None):
+def linear_backward_input(dy, layer, wname="weight", mask=None, out="f32", out_tensor=None, peer_out: int = 0):
     """dx = dy @ W^T (optionally * (mask > 0): the fused ReLU.backward) — nn/linear.py:60."""
     W = getattr(layer, wname).data
     d_in, d_out = W.shape
@@ -100,7 +101,7 @@ def linear_backward_input(dy, layer, wname="weight", mask=None, out="f32", out_t
         else:
             mk, ldm = mask, mask.shape[-1]
     ops.gemm(A, B, T, d_in, d_out, lda=lda, ldb=ldb, trans_b=True, C_out=dx, ldc=d_in, Cb_out=dxb, ldcb=d_in,
-             mask=mk, ldmask=ldm, mask_bits=bits)
+             mask=mk, ldmask=ldm, mask_bits=bits, Cb_peer=peer_out)
     return _result(dx, dxb)
 
 

@@ -28,21 +28,23 @@ class Linear(Layer):
 
     # `relu`, `mask` and `out` are the hooks MLP / Attention use to fuse ReLU into this layer's GEMM
     # epilogues and to keep GEMM-to-GEMM tensors in bf16 only (bf16 mode).
-    def forward(self, inputs, relu: bool = False, out: str = "f32", relu_bits=None, out_tensor=None):
+    def forward(self, inputs, relu: bool = False, out: str = "f32", relu_bits=None, out_tensor=None, peer_out: int = 0):
         """outputs = inputs @ W (+ b) — one GEMM with the bias (and ReLU) in its epilogue.
-        `out_tensor`: a preallocated bf16 buffer for the result (a peer-visible slot, distributed/peer.py)."""
+        `out_tensor` / `peer_out`: a preallocated bf16 buffer for the result and the address in the other
+        tensor-parallel rank's memory where every tile is stored as well (distributed/peer.py)."""
         bias = self.bias.data if self.use_bias else None
         outputs = F.linear_forward(inputs, self, "weight", bias=bias, relu=relu, out=out, relu_bits=relu_bits,
-                                   out_tensor=out_tensor)
+                                   out_tensor=out_tensor, peer_out=peer_out)
         self.ctx["inputs"] = inputs
         return outputs
 
-    def backward(self, d_out, mask=None, out: str = "f32", on_dx=None, out_tensor=None):
+    def backward(self, d_out, mask=None, out: str = "f32", on_dx=None, out_tensor=None, peer_out: int = 0):
         """dW = x^T dy (replaces, never accumulates), db = sum dy, returns dx = dy W^T.
         `on_dx(dx)` (optional) is called as soon as dx is enqueued — the tensor-parallel callers
         start their all-reduce there so it overlaps the dW / db kernels."""
         inputs = self.ctx.pop("inputs")
-        d_in = F.linear_backward_input(d_out, self, "weight", mask=mask, out=out, out_tensor=out_tensor)
+        d_in = F.linear_backward_input(d_out, self, "weight", mask=mask, out=out, out_tensor=out_tensor,
+                                       peer_out=peer_out)
         margin = TP_OVERLAP_SM_MARGIN if on_dx is not None else 0
         if on_dx is not None:
             on_dx(d_in)

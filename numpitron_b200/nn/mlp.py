@@ -40,9 +40,9 @@ class MLP(Model):
             if px is not None:
                 # no all-reduce: the partial goes to a peer-visible slot and the LayerNorm that follows adds
                 # the other rank's partial while it reads (distributed/peer.py)
-                slot, peer_ptr = px.slot("fwd", (*inputs.shape[:-1], self.row_linear.weight.data.shape[1]))
-                outputs = self.row_linear.forward(hidden, out="bf16", out_tensor=slot)
-                outputs._npt_peer = (px, peer_ptr)
+                slot, send_ptr, recv_ptr = px.slot("fwd", (*inputs.shape[:-1], self.row_linear.weight.data.shape[1]))
+                outputs = self.row_linear.forward(hidden, out="bf16", out_tensor=slot, peer_out=send_ptr)
+                outputs._npt_peer = (px, recv_ptr)
                 return outputs
             outputs = self.row_linear.forward(hidden, out="bf16" if out == "peer" else out)
             npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
@@ -56,9 +56,9 @@ class MLP(Model):
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
             px = peer.exchange(d_out.shape) if out == "peer" else None
             if px is not None:
-                slot, peer_ptr = px.slot("bwd", (*d_out.shape[:-1], self.column_linear.weight.data.shape[0]))
-                d_in = self.column_linear.backward(d_out, out="bf16", out_tensor=slot)
-                d_in._npt_peer = (px, peer_ptr)
+                slot, send_ptr, recv_ptr = px.slot("bwd", (*d_out.shape[:-1], self.column_linear.weight.data.shape[0]))
+                d_in = self.column_linear.backward(d_out, out="bf16", out_tensor=slot, peer_out=send_ptr)
+                d_in._npt_peer = (px, recv_ptr)
                 return d_in
             if out == "peer":
                 out = "bf16"

@@ -34,7 +34,7 @@ def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_of
          a_strides=(0, 0), b_strides=(0, 0), C_out=None, ldc=0, c_off=0, c_strides=(0, 0),
          Cb_out=None, ldcb=0, cb_off=0, cb_strides=(0, 0), batch=1, batch_inner=1, alpha=1.0,
          bias=None, relu=False, mask=None, ldmask=0, mask_off=0, mask_strides=(0, 0), mode=None,
-         relu_bits_out=None, mask_bits=None):
+         relu_bits_out=None, mask_bits=None, Cb_peer: int = 0):
     """C[b] = alpha * op(A[b]) op(B[b]) (+bias)(ReLU)(*mask>0) — see npt_gemm in the header.
 
     strides are (outer, inner) in elements.  A/B must be fp32 for mode 0 and bf16 for mode 1.
@@ -56,6 +56,9 @@ def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_of
     if Cb_out is not None:
         assert Cb_out.dtype == _BF16
         g.C_bf16, g.ldcb, g.stride_cb_outer, g.stride_cb_inner = _p(Cb_out, cb_off), ldcb, cb_strides[0], cb_strides[1]
+    if Cb_peer:
+        assert Cb_out is not None and C_out is None
+        g.C_bf16_peer = Cb_peer + 2 * cb_off
     g.alpha = alpha
     g.bias = _p(bias)
     g.relu = int(relu)
@@ -64,7 +67,7 @@ def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_of
         g.ldmask, g.stride_mask_outer, g.stride_mask_inner = ldmask, mask_strides[0], mask_strides[1]
     if relu_bits_out is not None or mask_bits is not None:
         bits = relu_bits_out if relu_bits_out is not None else mask_bits
-        assert bits.dtype == torch.int32 and bits.shape[-1] * 32 >= N
+        assert bits.dtype == torch.int32 and bits.shape[0] * 32 >= N and bits.shape[-1] >= M  # word-major [N/32][M]
         g.relu_bits_out, g.mask_bits, g.ld_bits = _p(relu_bits_out), _p(mask_bits), bits.shape[-1]
     need = lib.npt_gemm_workspace_bytes(C.byref(g))
     if need:
