@@ -8,6 +8,7 @@ can be regenerated.  Usage (from the repo root):
     python tests/golden/make_golden.py world 2 1     # tp=2 dp=1 tiny train steps (spawns ranks)
     python tests/golden/make_golden.py world 2 2     # tp=2 dp=2
     python tests/golden/make_golden.py curve         # config-1 shape, 100 steps, B=2 (slow)
+    python tests/golden/make_golden.py checkpoint    # a checkpoint file written by the reference + resumed step
 
 Nothing in `tests/` reads `/root/reference` at test time.
 """
@@ -275,6 +276,52 @@ def curve():
                             E_final=t.input_embedding.embedding.data)
 
 
+def checkpoint():
+    """the reference's own `checkpoint()` (train_shakespeare.py:30-41) writes the tiny model
+    after 2 training steps; the file is reloaded the way `train()` does (:87-93) and step 3 is run from
+    it.  Outputs: tiny_checkpoint.npy (the pickled state, as the reference wrote it), tiny_checkpoint_resaved.npy
+    (the same state loaded and saved again by the reference) and
+    tiny_checkpoint_resume.npz (batch, loss and embedding of the resumed step)."""
+    sys.path.insert(0, "/root/reference")
+    import train_shakespeare as ref_script
+    from numpitron import distributed as npdist
+    from numpitron.nn import Transformer, softmax_cross_entropy
+    from numpitron.optimizer import Adam
+
+    npdist.init(tp_size=1, dp_size=1)
+    t = Transformer(**TINY, rng=np.random.default_rng(42))
+    opt = Adam(t, 1e-4, 0.9, 0.99)
+    t.scatter()
+    opt.scatter()
+    batches = tiny_batches(3, TINY["vocab_size"], TINY_BATCH, TINY["seq_len"])
+    loss = None
+    for x, y in batches[:2]:
+        logits = t(x.copy())
+        loss, d = softmax_cross_entropy(logits, y.copy())
+        t.backward(d)
+        opt.step()
+    path = HERE / "tiny_checkpoint.npy"
+    ref_script.checkpoint(t, opt, 2, float(loss.mean()), path)
+    # resume exactly like train_shakespeare.py:87-93
+    state = np.load(path, allow_pickle=True)[()]
+    t2 = Transformer.from_dict(state["model_parameters"])
+    opt2 = Adam.from_dict(state["optimizer_parameters"], t2)
+    t2.scatter()
+    opt2.scatter()
+    # what the reference itself writes when it saves the reloaded state again (from_dict rebuilds the layers
+    # with weight_init="zeros", so those settings differ from the first file)
+    ref_script.checkpoint(t2, opt2, state["epoch"], state["validation_loss"], HERE / "tiny_checkpoint_resaved.npy")
+    x, y = batches[2]
+    logits = t2(x.copy())
+    loss3, d = softmax_cross_entropy(logits, y.copy())
+    t2.backward(d)
+    opt2.step()
+    np.savez_compressed(HERE / "tiny_checkpoint_resume.npz", x=x, y=y, loss=loss3, epoch=state["epoch"],
+                        validation_loss=state["validation_loss"], E_after=t2.input_embedding.embedding.data,
+                        wqkv_after_block1=t2.block_1.attention.qkv_projection.weight.data)
+    print("wrote tiny_checkpoint.npy", path.stat().st_size, "bytes; resumed loss", float(loss3.mean()))
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     if what == "layers":
@@ -285,3 +332,5 @@ if __name__ == "__main__":
         world_rank_main(int(sys.argv[2]), int(sys.argv[3]))
     elif what == "curve":
         curve()
+    elif what == "checkpoint":
+        checkpoint()

@@ -3,7 +3,7 @@ UNMODIFIED reference (tests/golden/make_golden.py).  literal=True must be bit-ex
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import GOLDEN, load_golden
 from oracle import numpitron_oracle as O
 
 TINY = dict(d_model=32, n_heads=4, n_layers=2, vocab=17, seq_len=16)
@@ -155,3 +155,18 @@ def test_tiny_world(golden_layers, tp, dp):
     if dp > 1:  # Q11: block weights diverge across DP replicas, the embedding does not
         eq(t.ranks[0][0].params["embedding"], t.ranks[1][0].params["embedding"])
         assert np.any(t.ranks[0][0].params["block_0.col.weight"] != t.ranks[1][0].params["block_0.col.weight"])
+
+
+def test_reference_checkpoint_fixture_layout():
+    """The checkpoint fixture written by the reference itself has the layout
+    numpitron_b200.checkpoint documents: nested settings / layers / parameters dicts of float32 arrays."""
+    state = np.load(GOLDEN / "tiny_checkpoint.npy", allow_pickle=True)[()]
+    assert list(state) == ["model_parameters", "optimizer_parameters", "epoch", "validation_loss"]
+    mp, op = state["model_parameters"], state["optimizer_parameters"]
+    assert list(mp) == ["settings", "layers"]
+    assert list(mp["layers"]) == ["input_embedding", "positional_encoding", "block_0", "block_1", "output_embedding"]
+    w = mp["layers"]["block_0"]["layers"]["attention"]["layers"]["qkv_projection"]["parameters"]["weight"]
+    assert w["data"].dtype == np.float32 and w["data"].shape == (32, 96) and w["shard_axis"] == 1 and w["gradient"] is None
+    assert list(op) == ["parameters", "timestep", "learning_rate", "beta1", "beta2", "eps"]
+    m = op["parameters"]["block_0"]["norm1"]["weight"]["parameters"]["momentum"]
+    assert m["data"].dtype == np.float32 and m["data"].shape == (32,)

@@ -163,3 +163,47 @@ def test_full_size_properties(precision):
     assert 20 < l1[0] < 40  # initial loss ~31 at this shape with the reference's init
     np.testing.assert_array_equal(np.float32(l1), np.float32(l2))
     np.testing.assert_array_equal(e1, e2)
+
+
+def _tree_equal(a, b, path="state"):
+    """Two checkpoint states are the same tree: same keys in the same order, same leaf types, dtypes,
+    shapes and (bit-exact) values."""
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and list(a.keys()) == list(b.keys()), (path, list(a), list(b) if isinstance(b, dict) else b)
+        for k in a:
+            _tree_equal(a[k], b[k], f"{path}[{k!r}]")
+    elif isinstance(a, np.ndarray):
+        assert isinstance(b, np.ndarray) and a.dtype == b.dtype and a.shape == b.shape, (path, a.dtype, getattr(b, "dtype", b))
+        np.testing.assert_array_equal(a, b, err_msg=path)
+    else:
+        assert type(a) is type(b) and a == b, (path, a, b)
+
+
+def test_checkpoint_interop_with_reference(tmp_path):
+    """SURVEY §8(f)1.  tests/golden/tiny_checkpoint.npy was written by the reference's own checkpoint()
+    after 2 training steps (make_golden.py checkpoint).  (1) It loads here, and saving it again from
+    here gives the tree the reference itself writes when it loads and re-saves that file
+    (tiny_checkpoint_resaved.npy) — every key, dtype, shape and value — so the reference can read our
+    files.  (2) The step resumed from it reproduces the reference's own resumed step."""
+    from numpitron_b200.checkpoint import load_checkpoint, save_checkpoint
+
+    src = GOLDEN / "tiny_checkpoint.npy"
+    want = np.load(src, allow_pickle=True)[()]
+    t, opt, epoch, vloss = load_checkpoint(src)
+    assert epoch == want["epoch"] and vloss == want["validation_loss"]
+    assert opt.timestep == want["optimizer_parameters"]["timestep"]
+    t.scatter()
+    opt.scatter()
+    out = tmp_path / "roundtrip.npy"
+    save_checkpoint(t, opt, epoch, vloss, out)
+    _tree_equal(np.load(GOLDEN / "tiny_checkpoint_resaved.npy", allow_pickle=True)[()], np.load(out, allow_pickle=True)[()])
+
+    with np.load(GOLDEN / "tiny_checkpoint_resume.npz") as z:
+        R = {k: z[k] for k in z.files}
+    logits = t(R["x"])
+    loss, d = softmax_cross_entropy(logits, R["y"])
+    t.backward(d)
+    opt.step()
+    close(loss, R["loss"], 1e-5)
+    close(t.input_embedding.embedding.data, R["E_after"], 1e-5)
+    close(t.block_1.attention.qkv_projection.weight.data, R["wqkv_after_block1"], 1e-5)
