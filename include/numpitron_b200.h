@@ -189,6 +189,11 @@ int npt_embedding_gather(const uint16_t* tokens, const float* E, int64_t ldE, co
                          int32_t chunk_start, int32_t chunk_end, int32_t masked, void* stream);
 /* out[t,:] = pos[t % S,:] + x[t,:]  (PositionalEncoding.forward, embedding.py:125-128); out may alias x. */
 int npt_add_pos(const float* x, const float* pos, float* out, void* out_bf16, int64_t T, int32_t S, int32_t d, void* stream);
+/* Data-loader windows (data/loader.py:49-54), SURVEY 8(f)2: the uint16 token file lives in HBM; for each of
+ * the B start indices (drawn on the host from the loader's NumPy generator, so the stream is the
+ * reference's) x[b,:] = tokens[start_b + 0..S-1], y[b,:] = tokens[start_b + 1..S].  start_b + S < n_tokens. */
+int npt_window_gather(const uint16_t* tokens, int64_t n_tokens, const int64_t* starts, uint16_t* x, uint16_t* y,
+                      int32_t B, int32_t S, void* stream);
 size_t npt_embedding_scatter_add_workspace_bytes(int64_t T, int32_t V_local);
 int npt_embedding_scatter_add(const uint16_t* tokens, const float* d_out, float* grad, int64_t ldG,
                               int64_t T, int32_t d, int32_t V_local, int32_t chunk_start,

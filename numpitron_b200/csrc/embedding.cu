@@ -181,6 +181,24 @@ struct SaLayout {
   }
 };
 
+
+// ---------------------------------------------------------------------------------------
+// Token windows of the data loader (data/loader.py:49-54): inputs = data[start + 0..S-1],
+// labels = data[start + 1 .. start + S], for B random starts, from a token file that was staged in
+// HBM once.  Pure index work on uint16: bit-exact by construction.
+__global__ void __launch_bounds__(256)
+window_gather_kernel(const uint16_t* __restrict__ tokens, const int64_t* __restrict__ starts,
+                     uint16_t* __restrict__ x, uint16_t* __restrict__ y, int B, int S) {
+  pdl_wait();
+  pdl_trigger();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * S) return;
+  const int b = (int)(i / S), s = (int)(i - (int64_t)b * S);
+  const int64_t src = starts[b] + s;
+  x[i] = tokens[src];
+  y[i] = tokens[src + 1];
+}
+
 }  // namespace npt
 
 using namespace npt;
@@ -242,6 +260,18 @@ int npt_embedding_scatter_add(const uint16_t* tokens, const float* d_out, float*
   NPT_LAUNCH_CHECK();
   dim3 grid((unsigned)V_local, (unsigned)cdiv(d, 128));
   NPT_CHECK_CUDA(launch_pdl(sa_accumulate_kernel, dim3(grid), dim3(128), 0, st, offsets, order, d_out, grad, ldG, d));
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int npt_window_gather(const uint16_t* tokens, int64_t n_tokens, const int64_t* starts, uint16_t* x, uint16_t* y,
+                      int32_t B, int32_t S, void* stream) {
+  NPT_REQUIRE(B >= 0 && S > 0 && n_tokens >= (int64_t)S + 2, "window_gather: bad shape B=%d S=%d n_tokens=%lld", B, S,
+              (long long)n_tokens);
+  if (B == 0) return 0;
+  const int64_t n = (int64_t)B * S;
+  NPT_CHECK_CUDA(launch_pdl(window_gather_kernel, dim3((unsigned)cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, tokens,
+                            starts, x, y, B, S));
   NPT_LAUNCH_CHECK();
   return 0;
 }

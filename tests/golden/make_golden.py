@@ -9,6 +9,7 @@ can be regenerated.  Usage (from the repo root):
     python tests/golden/make_golden.py world 2 2     # tp=2 dp=2
     python tests/golden/make_golden.py curve         # config-1 shape, 100 steps, B=2 (slow)
     python tests/golden/make_golden.py checkpoint    # a checkpoint file written by the reference + resumed step
+    python tests/golden/make_golden.py loader        # batches of the reference DataLoader on a synthetic token file
 
 Nothing in `tests/` reads `/root/reference` at test time.
 """
@@ -276,6 +277,35 @@ def curve():
                             E_final=t.input_embedding.embedding.data)
 
 
+LOADER_TOKENS = dict(seed=1234, vocab=17, n=5000)   # the synthetic uint16 token file of the loader fixture
+LOADER_CFG = dict(seq_len=16, batch_size=4, rng_seed=5)
+
+
+def loader():
+    """the first 6 batches and the epoch length of the reference's DataLoader
+    (data/loader.py) on a synthetic token file that the test regenerates from LOADER_TOKENS."""
+    import tempfile
+
+    from numpitron import distributed as npdist
+    from numpitron.data import DataLoader
+
+    npdist.init(tp_size=1, dp_size=1)
+    data = np.random.default_rng(LOADER_TOKENS["seed"]).integers(0, LOADER_TOKENS["vocab"], LOADER_TOKENS["n"]).astype(np.uint16)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / "tokens.bin"
+        data.tofile(path)
+        dl = DataLoader(path, LOADER_CFG["seq_len"], LOADER_CFG["batch_size"], np.random.default_rng(LOADER_CFG["rng_seed"]))
+        G = {"batches_per_epoch": np.int64(dl.batches_per_epoch)}
+        n_epoch = 0
+        for i, (x, y) in enumerate(dl.iter_epoch()):
+            n_epoch += 1
+            if i < 6:
+                G[f"x{i}"], G[f"y{i}"] = np.array(x), np.array(y)
+        G["batches_yielded_per_epoch"] = np.int64(n_epoch)
+    np.savez_compressed(HERE / "loader_tp1.npz", **G)
+    print("wrote loader_tp1.npz", int(G["batches_per_epoch"]), n_epoch)
+
+
 def checkpoint():
     """the reference's own `checkpoint()` (train_shakespeare.py:30-41) writes the tiny model
     after 2 training steps; the file is reloaded the way `train()` does (:87-93) and step 3 is run from
@@ -334,3 +364,5 @@ if __name__ == "__main__":
         curve()
     elif what == "checkpoint":
         checkpoint()
+    elif what == "loader":
+        loader()

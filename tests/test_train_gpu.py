@@ -207,3 +207,35 @@ def test_checkpoint_interop_with_reference(tmp_path):
     close(loss, R["loss"], 1e-5)
     close(t.input_embedding.embedding.data, R["E_after"], 1e-5)
     close(t.block_1.attention.qkv_projection.weight.data, R["wqkv_after_block1"], 1e-5)
+
+
+def test_device_dataloader_matches_reference(tmp_path):
+    """SURVEY §8(f)2.  The device-resident DataLoader (token file in HBM, start indices from the same NumPy
+    generator, windows cut by npt_window_gather) yields the reference DataLoader's batches bit for bit
+    (tests/golden/loader_tp1.npz, written by the reference's own loader), the same number of batches per
+    epoch, and its batches feed train_step directly."""
+    from numpitron_b200.data import DataLoader
+
+    with np.load(GOLDEN / "loader_tp1.npz") as z:
+        G = {k: z[k] for k in z.files}
+    data = np.random.default_rng(1234).integers(0, 17, 5000).astype(np.uint16)   # make_golden.LOADER_TOKENS
+    path = tmp_path / "tokens.bin"
+    data.tofile(path)
+    dl = DataLoader(path, 16, 4, np.random.default_rng(5))
+    assert dl.batches_per_epoch == int(G["batches_per_epoch"])
+    n = 0
+    for i, (x, y) in enumerate(dl.iter_epoch()):
+        n += 1
+        assert x.is_cuda and x.dtype == torch.uint16 and tuple(x.shape) == (4, 16)
+        if i < 6:
+            np.testing.assert_array_equal(x.view(torch.int16).cpu().numpy().view(np.uint16), G[f"x{i}"])
+            np.testing.assert_array_equal(y.view(torch.int16).cpu().numpy().view(np.uint16), G[f"y{i}"])
+    assert n == int(G["batches_yielded_per_epoch"])
+    # the device batches are what the layers take: one train step from them equals the step from host arrays
+    t1, o1 = build(TINY)
+    t2, o2 = build(TINY)
+    dl2 = DataLoader(path, 16, 4, np.random.default_rng(5))
+    xd, yd = dl2.next_batch()
+    l_dev = train_step(t1, o1, xd, yd)
+    l_host = train_step(t2, o2, G["x0"], G["y0"])
+    assert l_dev == l_host
