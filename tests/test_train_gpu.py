@@ -239,3 +239,20 @@ def test_device_dataloader_matches_reference(tmp_path):
     l_dev = train_step(t1, o1, xd, yd)
     l_host = train_step(t2, o2, G["x0"], G["y0"])
     assert l_dev == l_host
+
+
+def test_sampling_matches_reference():
+    """SURVEY §8(f)3.  Tokens generated from the reference-written checkpoint with the reference's samplers
+    (tests/golden/sample_tp1.npz: 24 tokens from a 1-token prompt, so the 16-token context window slides)
+    — greedy, and temperature sampling with the same NumPy generator — are reproduced token for token in
+    the fp32 mode."""
+    from numpitron_b200.checkpoint import load_checkpoint
+    from numpitron_b200.sample import generate
+
+    with np.load(GOLDEN / "sample_tp1.npz") as z:
+        G = {k: z[k] for k in z.files}
+    t, _, _, _ = load_checkpoint(GOLDEN / "tiny_checkpoint.npy")
+    t.scatter()
+    assert generate(t, [3], 24, None, None, 17) == G["greedy"].tolist()
+    for name, temp in (("basic_t1", 1.0), ("basic_t40", 40.0)):
+        assert generate(t, [3], 24, temp, np.random.default_rng(42), 17) == G[name].tolist(), name
