@@ -89,9 +89,15 @@ typedef struct npt_gemm_args {
    * nn/mlp.py:34) lands next to the peer's own partial while the GEMM is still running, and the LayerNorm
    * that follows adds the two from local memory (npt_layernorm_fwd_v2, x_peer). */
   void* C_bf16_peer;
+  /* 1: when the launch is split along K (npt_gemm_splits() > 1) leave the fp32 partials
+   * [split][batch][M][N] in `workspace` and do NOT reduce them into C — the consumer adds them in split
+   * order (npt_adam_tensor.g_splits: the weight gradients of nn/linear.py:55 are only ever read by Adam,
+   * so the reduce pass, one launch per weight, disappears).  No effect on launches that are not split. */
+  int32_t skip_splitk_reduce;
 } npt_gemm_args;
 
 size_t npt_gemm_workspace_bytes(const npt_gemm_args* args);
+int32_t npt_gemm_splits(const npt_gemm_args* args);   /* split-K factor npt_gemm will use for these arguments */
 int npt_gemm(const npt_gemm_args* args, void* stream);
 
 /* fp32 -> bf16 copy of a rows x cols matrix; columns [cols, ld_dst) of dst are zero-filled. */
@@ -234,6 +240,9 @@ typedef struct npt_adam_tensor {
   void* p_bf16;            /* optional bf16 shadow of p refreshed in the same pass (may be NULL) */
   int64_t n;               /* elements */
   int64_t shadow_cols, shadow_ld;  /* if p_bf16: p is rows x shadow_cols, shadow row pitch shadow_ld */
+  /* g_splits > 1: g holds split-K partials, gradient[i] = ((0 + g[i]) + g[stride + i]) + ... in split order
+   * (the exact additions of the split-K reduce kernel, so the update is bit-identical to reducing first). */
+  int64_t g_splits, g_split_stride;
 } npt_adam_tensor;
 int npt_adam_step(const npt_adam_tensor* tensors_dev, const npt_adam_tensor* tensors_host,
                   int32_t n_tensors, float lr, float b1, float omb1, float b2, float omb2,

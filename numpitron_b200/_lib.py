@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("relu_bits_out", c_void_p), ("mask_bits", c_void_p), ("ld_bits", c_int64),
         ("C_bf16_peer", c_void_p),
+        ("skip_splitk_reduce", c_int32),
     ]
 
 
@@ -46,6 +47,7 @@ class AdamTensor(C.Structure):
     _fields_ = [
         ("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p),
         ("p_bf16", c_void_p), ("n", c_int64), ("shadow_cols", c_int64), ("shadow_ld", c_int64),
+        ("g_splits", c_int64), ("g_split_stride", c_int64),
     ]
 
 
@@ -66,6 +68,7 @@ _SIGNATURES = {
     "npt_layernorm_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "npt_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P, c_size_t, _P]),
     "npt_layernorm_bwd_colsum_supported": (c_int, [c_int32]),
+    "npt_gemm_splits": (c_int32, [_P]),
     "npt_window_gather": (c_int, [_P, c_int64, _P, _P, _P, c_int32, c_int32, _P]),
     "npt_layernorm_bf16_input_supported": (c_int, [c_int32]),
     "npt_layernorm_fwd_v2": (c_int, [_P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P]),

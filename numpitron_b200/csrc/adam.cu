@@ -27,6 +27,35 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
   return p;
 }
 
+// gradient element(s) i of tensor t: plain, or the sum of its split-K partials in split order — the same
+// additions, starting from 0, as splitk_reduce_*_kernel (gemm.cu), so nothing changes bit-wise
+__device__ __forceinline__ float4 adam_grad4(const npt_adam_tensor& t, int64_t i4) {
+  if (t.g_splits <= 1) return ld_stream(reinterpret_cast<const float4*>(t.g) + i4);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* g0 = reinterpret_cast<const float4*>(t.g) + i4;
+  const int64_t st4 = t.g_split_stride >> 2;  // the vector path requires a stride that is a multiple of 4
+  int64_t s = 0;
+  for (; s + 4 <= t.g_splits; s += 4) {  // four independent loads in flight, additions in split order
+    const float4 a0 = ld_stream(g0 + s * st4), a1 = ld_stream(g0 + (s + 1) * st4);
+    const float4 a2 = ld_stream(g0 + (s + 2) * st4), a3 = ld_stream(g0 + (s + 3) * st4);
+    acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;
+    acc.x += a1.x; acc.y += a1.y; acc.z += a1.z; acc.w += a1.w;
+    acc.x += a2.x; acc.y += a2.y; acc.z += a2.z; acc.w += a2.w;
+    acc.x += a3.x; acc.y += a3.y; acc.z += a3.z; acc.w += a3.w;
+  }
+  for (; s < t.g_splits; ++s) {
+    const float4 a = ld_stream(g0 + s * st4);
+    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+  }
+  return acc;
+}
+__device__ __forceinline__ float adam_grad1(const npt_adam_tensor& t, int64_t i) {
+  if (t.g_splits <= 1) return t.g[i];
+  float acc = 0.f;
+  for (int64_t s = 0; s < t.g_splits; ++s) acc += t.g[s * t.g_split_stride + i];
+  return acc;
+}
+
 __global__ void __launch_bounds__(kAdamThreads)
 adam_multi_kernel(const npt_adam_tensor* __restrict__ tensors, int n_tensors, AdamScalars s) {
   pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
@@ -45,14 +74,15 @@ adam_multi_kernel(const npt_adam_tensor* __restrict__ tensors, int n_tensors, Ad
   int64_t hi = lo + kAdamChunk;
   if (hi > t.n) hi = t.n;
   __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(t.p_bf16);
-  const bool vec = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
+  const bool vec = (t.g_splits <= 1 || (t.g_split_stride & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
                      reinterpret_cast<uintptr_t>(t.m) | reinterpret_cast<uintptr_t>(t.v)) & 15u) == 0 &&
                    (!pb || (t.shadow_cols == t.shadow_ld && (reinterpret_cast<uintptr_t>(pb) & 7u) == 0));
   if (vec) {
     const int64_t v_lo = lo >> 2, v_hi = hi >> 2;  // lo is a multiple of 4
     for (int64_t i = v_lo + threadIdx.x; i < v_hi; i += kAdamThreads) {
       float4 p = reinterpret_cast<float4*>(t.p)[i];
-      const float4 g = ld_stream(reinterpret_cast<const float4*>(t.g) + i);
+      const float4 g = adam_grad4(t, i);
       float4 m = reinterpret_cast<float4*>(t.m)[i];
       float4 v = reinterpret_cast<float4*>(t.v)[i];
       adam_one(p.x, g.x, m.x, v.x, s);
@@ -66,14 +96,14 @@ adam_multi_kernel(const npt_adam_tensor* __restrict__ tensors, int n_tensors, Ad
     }
     for (int64_t i = (v_hi << 2) + threadIdx.x; i < hi; i += kAdamThreads) {
       float p = t.p[i], m = t.m[i], v = t.v[i];
-      adam_one(p, t.g[i], m, v, s);
+      adam_one(p, adam_grad1(t, i), m, v, s);
       t.p[i] = p; t.m[i] = m; t.v[i] = v;
       if (pb) pb[i] = __float2bfloat16_rn(p);
     }
   } else {
     for (int64_t i = lo + threadIdx.x; i < hi; i += kAdamThreads) {
       float p = t.p[i], m = t.m[i], v = t.v[i];
-      adam_one(p, t.g[i], m, v, s);
+      adam_one(p, adam_grad1(t, i), m, v, s);
       t.p[i] = p; t.m[i] = m; t.v[i] = v;
       if (pb) {
         const int64_t r = i / t.shadow_cols, c = i - r * t.shadow_cols;

@@ -114,6 +114,11 @@ size_t npt_gemm_workspace_bytes(const npt_gemm_args* a) {
   return (size_t)splits * (size_t)a->batch * (size_t)a->M * (size_t)a->N * sizeof(float);
 }
 
+int32_t npt_gemm_splits(const npt_gemm_args* args) {
+  if (!args) return 1;
+  return (int32_t)choose_splits(*args);
+}
+
 int npt_gemm(const npt_gemm_args* args, void* stream) {
   NPT_REQUIRE(args != nullptr, "gemm: null args");
   const npt_gemm_args& a = *args;
@@ -150,7 +155,7 @@ int npt_gemm(const npt_gemm_args* args, void* stream) {
   int rc = (a.mode == NPT_GEMM_FP32_SIMT) ? gemm_simt_launch(a, epi, splits, partial, st)
                                           : gemm_tc_launch(a, epi, splits, partial, st);
   if (rc) return rc;
-  if (splits > 1) {
+  if (splits > 1 && !a.skip_splitk_reduce) {
     if (a.N % 4 == 0 && aligned16(partial) && a.batch <= 65535 && cdiv(a.M, 8) <= 65535) {
       dim3 grid((unsigned)cdiv(a.N / 4, 32), (unsigned)cdiv(a.M, 8), (unsigned)a.batch);
       NPT_CHECK_CUDA(launch_pdl(splitk_reduce_vec_kernel, grid, dim3(32, 8), 0, st, partial, epi, splits, a.batch));

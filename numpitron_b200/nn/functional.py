@@ -75,15 +75,18 @@ def linear_forward(x, layer, wname="weight", bias=None, relu=False, out="f32", r
     return _result(y, yb)
 
 
-def linear_backward_weight(x, dy):
-    """dW = x^T @ dy over all tokens — einsum("bsd,bsh->dh"), nn/linear.py:55."""
+def linear_backward_weight(x, dy, may_defer: bool = False):
+    """dW = x^T @ dy over all tokens — einsum("bsd,bsh->dh"), nn/linear.py:55.
+    `may_defer` (and rt.deferred_wgrad active): a split-K launch leaves its partials for Adam to add, and
+    the returned gradient is that (splits, d_in, d_out) tensor tagged `_npt_splits`."""
     d_in, d_out = x.shape[-1], dy.shape[-1]
     T = x.numel() // d_in
     A, lda = _act(x)
     B, ldb = _act(dy)
     dW = rt.empty((d_in, d_out))
-    ops.gemm(A, B, d_in, d_out, T, lda=lda, ldb=ldb, trans_a=True, C_out=dW, ldc=d_out)
-    return dW
+    partials = ops.gemm(A, B, d_in, d_out, T, lda=lda, ldb=ldb, trans_a=True, C_out=dW, ldc=d_out,
+                        skip_reduce=may_defer and rt.defer_wgrad())
+    return dW if partials is None else partials
 
 
 def linear_backward_input(dy, layer, wname="weight", mask=None, out="f32", out_tensor=None, peer_out: int = 0):

@@ -50,7 +50,7 @@ class Linear(Layer):
             on_dx(d_in)
         if margin:
             ops.set_sm_margin(margin)  # leave SMs for the all-reduce next to the dW GEMM
-        self.update_parameter("weight", gradient=F.linear_backward_weight(inputs, d_out))
+        self.update_parameter("weight", gradient=F.linear_backward_weight(inputs, d_out, may_defer=True))
         if self.use_bias:
             self.update_parameter("bias", gradient=F.bias_grad(d_out))
         if margin:

@@ -34,10 +34,13 @@ def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_of
          a_strides=(0, 0), b_strides=(0, 0), C_out=None, ldc=0, c_off=0, c_strides=(0, 0),
          Cb_out=None, ldcb=0, cb_off=0, cb_strides=(0, 0), batch=1, batch_inner=1, alpha=1.0,
          bias=None, relu=False, mask=None, ldmask=0, mask_off=0, mask_strides=(0, 0), mode=None,
-         relu_bits_out=None, mask_bits=None, Cb_peer: int = 0):
+         relu_bits_out=None, mask_bits=None, Cb_peer: int = 0, skip_reduce: bool = False):
     """C[b] = alpha * op(A[b]) op(B[b]) (+bias)(ReLU)(*mask>0) — see npt_gemm in the header.
 
     strides are (outer, inner) in elements.  A/B must be fp32 for mode 0 and bf16 for mode 1.
+    `skip_reduce`: if the launch is split along K, the fp32 partials stay in a fresh (splits, M, N) tensor,
+    C is not written, and that tensor is returned (tagged `_npt_splits`) for a consumer that adds them
+    itself (Adam); otherwise None is returned.
     """
     lib = _lib_()
     mode = rt.gemm_mode() if mode is None else mode
@@ -70,12 +73,20 @@ def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_of
         assert bits.dtype == torch.int32 and bits.shape[0] * 32 >= N and bits.shape[-1] >= M  # word-major [N/32][M]
         g.relu_bits_out, g.mask_bits, g.ld_bits = _p(relu_bits_out), _p(mask_bits), bits.shape[-1]
     need = lib.npt_gemm_workspace_bytes(C.byref(g))
+    partials = None
     if need:
-        ws = rt.workspace(need)
-        g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
+        splits = int(lib.npt_gemm_splits(C.byref(g))) if (skip_reduce and batch == 1) else 1
+        if splits > 1:
+            partials = rt.empty((splits, M, N))       # owned by the caller from here on (not the shared scratch)
+            partials._npt_splits = splits
+            assert partials.numel() * 4 >= need
+            g.workspace, g.workspace_bytes, g.skip_splitk_reduce = partials.data_ptr(), partials.numel() * 4, 1
+        else:
+            ws = rt.workspace(need)
+            g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
     if GEMM_PROFILE is None:
         check(lib.npt_gemm(C.byref(g), rt.stream()), "npt_gemm")
-        return
+        return partials
     # bench.py's roofline leg: CUDA events around this launch, on the launching stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -83,6 +94,7 @@ def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_of
     e1.record()
     GEMM_PROFILE.append(dict(events=(e0, e1), flops=2.0 * M * N * K * batch, M=M, N=N, K=K, batch=batch,
                              trans=(int(trans_a), int(trans_b)), mode=mode, splitk=bool(need)))
+    return partials
 
 
 GEMM_PROFILE = None  # set to a list to collect per-launch timings
@@ -407,6 +419,8 @@ class AdamTable:
             t = self.host[i]
             t.p, t.g, t.m, t.v = _p(p), _p(g), _p(m), _p(v)
             t.n = p.numel()
+            t.g_splits = getattr(g, "_npt_splits", 1)   # split-K partials left by a weight-gradient GEMM
+            t.g_split_stride = p.numel()
             if sh is not None:
                 t.p_bf16 = _p(sh)
                 t.shadow_cols = p.shape[-1]

@@ -107,6 +107,27 @@ def ptr(t, offset_elems: int = 0) -> int:
     return t.data_ptr() + offset_elems * t.element_size()
 
 
+class deferred_wgrad:
+    """Context manager: inside it, Linear.backward leaves the split-K partials of its weight-gradient GEMM
+    un-reduced and hands them to Adam, which adds them while it reads (same additions, same order: the
+    update is bit-identical).  Used by GraphedTrainStep, where nothing else looks at those gradients
+    between backward and the optimizer step; `parameter.gradient` is then a (splits, d_in, d_out) tensor
+    tagged `_npt_splits`."""
+
+    def __enter__(self):
+        self.prev = _state.get("defer_wgrad", False)
+        _state["defer_wgrad"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _state["defer_wgrad"] = self.prev
+        return False
+
+
+def defer_wgrad() -> bool:
+    return bool(_state.get("defer_wgrad", False))
+
+
 def workspace(nbytes: int) -> torch.Tensor:
     """A scratch buffer of at least `nbytes` (stream-ordered reuse; grown on demand)."""
     nbytes = max(int(nbytes), 256)

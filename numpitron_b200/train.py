@@ -68,7 +68,9 @@ class GraphedTrainStep:
 
     # -- bodies -----------------------------------------------------------------------------------
     def _compute(self):
-        loss = train_step_device(self.transformer, self.optimizer, self.x_dev, self.y_dev)
+        # nothing reads the weight gradients between backward and Adam here: skip their split-K reduce
+        with rt.deferred_wgrad():
+            loss = train_step_device(self.transformer, self.optimizer, self.x_dev, self.y_dev)
         ops.check(_lib.load().npt_memcpy_async(self.loss_dev.data_ptr(), loss.data_ptr(), 4, 3, rt.stream()),
                   "npt_memcpy_async")
 

@@ -499,6 +499,44 @@ def test_adam_multi_tensor_bit_exact_vs_oracle():
             assert not got[:, p.shape[1]:].any()
 
 
+@pytest.mark.parametrize("d_in,d_out", [(384, 1152), (384, 384), (1536, 384), (104, 72)])
+def test_adam_consumes_splitk_partials_bit_exact(d_in, d_out):
+    """Weight gradient dW = x^T dy of a Linear (nn/linear.py:55) as a split-K tcgen05 GEMM: with
+    rt.deferred_wgrad the partials are not reduced; Adam adds them in split order while it reads.  The
+    parameters, moments and the bf16 shadow must come out bit-identical to reducing first."""
+    from numpitron_b200.nn import functional as F
+
+    T = 8192
+    g = torch.Generator(device="cuda").manual_seed(d_in + d_out)
+    x = torch.randn((1, T, d_in), device="cuda", generator=g).bfloat16()
+    dy = (torch.randn((1, T, d_out), device="cuda", generator=g) * 0.01).bfloat16()
+    rt.set_precision("bf16")
+    try:
+        dW = F.linear_backward_weight(x, dy)
+        with rt.deferred_wgrad():
+            parts = F.linear_backward_weight(x, dy, may_defer=True)
+        assert getattr(parts, "_npt_splits", 1) > 1 and tuple(parts.shape) == (parts._npt_splits, d_in, d_out)
+        np.testing.assert_array_equal(host(parts).sum(0, dtype=np.float64).astype(np.float32).shape, host(dW).shape)
+        f = lambda v: float(np.float32(v))
+        rng = np.random.default_rng(3)
+        out = []
+        for grad in (dW, parts):
+            p = dev(rng.standard_normal((d_in, d_out)).astype(np.float32)) if not out else dev(p0)
+            if not out:
+                p0, m0, v0 = host(p).copy(), (rng.standard_normal((d_in, d_out)) * 0.01).astype(np.float32), \
+                    (rng.random((d_in, d_out)) * 0.01).astype(np.float32)
+            m, v = dev(m0), dev(v0)
+            sh = ops.cast_bf16(p, pad_cols=True)
+            table = ops.AdamTable(1)
+            table.fill([(p, grad, m, v, sh)])
+            ops.adam_step(table, f(1e-4), f(0.9), f(1 - 0.9), f(0.99), f(1 - 0.99), f(1 - 0.9), f(1 - 0.99), f(1e-7))
+            out.append((host(p), host(m), host(v), host(sh)))
+        for a, b in zip(out[0], out[1]):
+            np.testing.assert_array_equal(a, b)
+    finally:
+        rt.set_precision("fp32")
+
+
 # ---------------------------------------------------------------------------------------------
 # edge cases: empty inputs, the uint16 token range, error reporting through the C ABI
 # ---------------------------------------------------------------------------------------------
