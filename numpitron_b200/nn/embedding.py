@@ -41,11 +41,15 @@ class InputEmbedding(Layer):
             return npdist.get_var("embedding_chunk_start"), npdist.get_var("embedding_chunk_end")
         return 0, self.embedding.data.shape[1]  # un-scattered: the mask is computed but unused
 
-    def forward(self, inputs):
-        """inputs (B,S) uint16 tokens -> (B,S,d); out-of-chunk tokens give zero rows."""
+    def forward(self, inputs, pos=None):
+        """inputs (B,S) uint16 tokens -> (B,S,d); out-of-chunk tokens give zero rows.
+        `pos`: the positional-encoding table; when given (Transformer.forward at tp = 1, where no all-reduce
+        sits between the two layers) `encoding + x` of PositionalEncoding.forward (embedding.py:125-128) is
+        done by the same kernel, with the same single fp32 addition."""
         lo, hi = self._bounds()
         seq_len = inputs.shape[-1]
-        outputs = ops.embedding_gather(inputs, self.embedding.data, None, seq_len, lo, hi, self.is_scattered)
+        outputs = ops.embedding_gather(inputs, self.embedding.data, pos, seq_len, lo, hi, self.is_scattered,
+                                       want_bf16=pos is not None and rt.is_bf16())
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
             npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
         self.ctx["inputs"] = inputs

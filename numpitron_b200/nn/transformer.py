@@ -21,6 +21,17 @@ class Transformer(Model):
             self.add_layer(f"block_{layer}", block())
         self.add_layer("output_embedding", OutputEmbedding(self.input_embedding))  # tied
 
+    def forward(self, inputs):
+        """Model.forward (nn/model.py:15-18).  Without tensor parallelism nothing sits between the embedding
+        gather and the positional add, so both run in one kernel (same arithmetic, one pass less)."""
+        if npdist.tensor_parallel_size() > 1:
+            return super().forward(inputs)
+        layers = list(self.layers.values())
+        outputs = self.input_embedding.forward(inputs, pos=self.positional_encoding.encoding)
+        for layer in layers[2:]:
+            outputs = layer(outputs)
+        return outputs
+
     def backward(self, d_out):
         """Reverse pass; after each TOP-LEVEL layer its own parameters are all-reduced (SUM) over the
         data-parallel group — which in practice is only the tied embedding gradient, because a
