@@ -56,6 +56,27 @@ add_pos_kernel(const float* x, const float* __restrict__ pos, float* out, __nv_b
   }
 }
 
+// d % 4 == 0, 16-byte aligned buffers: a warp per token row, 128-bit accesses, no per-element division
+__global__ void __launch_bounds__(256)
+add_pos_vec_kernel(const float* x, const float* __restrict__ pos, float* out, __nv_bfloat16* __restrict__ xb,
+                   int64_t T, int S, int d) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + t * d);
+  const float4* pr = reinterpret_cast<const float4*>(pos + (int64_t)(t % S) * d);
+  float4* orow = reinterpret_cast<float4*>(out + t * d);
+  for (int c = lane; c < (d >> 2); c += 32) {
+    const float4 a = xr[c], p = __ldg(pr + c);
+    float4 v;
+    v.x = __fadd_rn(p.x, a.x); v.y = __fadd_rn(p.y, a.y); v.z = __fadd_rn(p.z, a.z); v.w = __fadd_rn(p.w, a.w);
+    orow[c] = v;
+    if (xb) st_bf16x4(xb + t * d + (int64_t)c * 4, v);
+  }
+}
+
 // ---- scatter-add ------------------------------------------------------------------------------
 constexpr int kSaChunk = 256;
 
@@ -219,6 +240,12 @@ int npt_embedding_gather(const uint16_t* tokens, const float* E, int64_t ldE, co
 
 int npt_add_pos(const float* x, const float* pos, float* out, void* x_bf16, int64_t T, int32_t S, int32_t d, void* stream) {
   if (T <= 0) return 0;
+  if (d % 4 == 0 && aligned16(x) && aligned16(pos) && aligned16(out) && (!x_bf16 || aligned8(x_bf16))) {
+    NPT_CHECK_CUDA(launch_pdl(add_pos_vec_kernel, dim3((unsigned)cdiv(T, 8)), dim3(256), 0, (cudaStream_t)stream, x, pos, out,
+                              (__nv_bfloat16*)x_bf16, T, S, d));
+    NPT_LAUNCH_CHECK();
+    return 0;
+  }
   int64_t blocks = cdiv(T * d, 256);
   int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
