@@ -80,7 +80,11 @@ class OutputEmbedding(Layer):
     def backward(self, d_out):
         self.input_embedding.update_parameter(
             "embedding", gradient=F.linear_backward_weight(self.ctx.pop("inputs"), d_out))
-        d_out = F.linear_backward_input(d_out, self.input_embedding, "embedding")  # d @ E^T
+        # d @ E^T.  In bf16 mode this dX is read by the last block's LayerNorm backward, which takes bf16
+        # (the value it would otherwise be cast to): let the GEMM epilogue write bf16 directly.
+        d_model = self.input_embedding.embedding.data.shape[0]
+        out = "bf16" if rt.is_bf16() and ops.layernorm_bf16_input_supported(d_model) else "f32"
+        d_out = F.linear_backward_input(d_out, self.input_embedding, "embedding", out=out)
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
             npdist.all_reduce(d_out, group=npdist.tensor_parallel_group())
         return d_out
