@@ -98,3 +98,24 @@ def test_token_ids_must_fit_uint16():
         _host_to_device(np.array([[0, 70000]], dtype=np.int64))
     with pytest.raises(ValueError, match="uint16"):
         _host_to_device(np.array([[-1, 3]], dtype=np.int64))
+
+
+@pytest.mark.parametrize("M,N", [(384, 1152), (384, 384), (384, 1536), (1536, 384)])
+def test_weight_gradient_split_factor_is_one_wave(M, N):
+    """npt_gemm_splits (host-only): the weight-gradient GEMMs of the Shakespeare shape (K = 16 384 tokens)
+    must split into a number of units that fits ONE wave of the 148 SMs.  (The first version rounded the
+    factor up — 18 tiles x 9 splits = 162 units = two waves — which cost 6 % of the step.)"""
+    lib = _lib.load()
+    g = _lib.GemmArgs()
+    g.mode, g.trans_a, g.M, g.N, g.K, g.batch, g.batch_inner = 1, 1, M, N, 16384, 1, 1
+    splits = lib.npt_gemm_splits(C.byref(g))
+    assert splits > 1
+    need = lib.npt_gemm_workspace_bytes(C.byref(g))
+    assert need == splits * M * N * 4
+    # tile widths the kernel can pick: 128 / 192 / 256 columns, 128 rows
+    tiles_by_width = {bn: -(-M // 128) * -(-N // bn) for bn in (128, 192, 256)}
+    assert any(t * splits <= 148 for t in tiles_by_width.values()), (splits, tiles_by_width)
+    assert splits * 4 <= 16384 // 64          # at least 4 k-blocks per split
+    # a launch that already fills the GPU is not split
+    g.trans_a, g.M, g.N, g.K = 0, 16384, 1536, 384
+    assert lib.npt_gemm_splits(C.byref(g)) == 1
