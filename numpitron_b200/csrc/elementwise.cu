@@ -121,7 +121,7 @@ colsum_stage1_kernel(const void* __restrict__ xv, int x_is_bf16, int64_t ld, flo
   }
 }
 // Vectorised stage 1: each thread owns 4 adjacent columns (16-byte fp32 / 8-byte bf16 loads),
-// block = 32 column groups (128 columns) x 8 row lanes, 4 rows in flight per lane.  The last block to
+// block = 32 column groups (128 columns) x 8 row lanes, 8 rows in flight per lane.  The last block to
 // finish a 128-column strip (ticket counter per strip) adds the strip's partial rows in fixed order
 // and writes the result, so the sum does not depend on which block that is and no second launch is
 // needed.  The counters return to zero for the next launch (one stream at a time, like the workspace).
@@ -151,6 +151,14 @@ colsum_stage1_vec_kernel(const void* __restrict__ xv, int64_t ld, float* __restr
   };
   if (col < cols) {
     int64_t r = r0 + ry;
+    for (; r + 56 < r1; r += 64) {  // 8 rows in flight per thread: the kernel is bound by bytes in flight
+      const float4 a = load(r), b = load(r + 8), c = load(r + 16), e = load(r + 24);
+      const float4 f = load(r + 32), g = load(r + 40), h = load(r + 48), k = load(r + 56);
+      acc.x += ((a.x + b.x) + (c.x + e.x)) + ((f.x + g.x) + (h.x + k.x));
+      acc.y += ((a.y + b.y) + (c.y + e.y)) + ((f.y + g.y) + (h.y + k.y));
+      acc.z += ((a.z + b.z) + (c.z + e.z)) + ((f.z + g.z) + (h.z + k.z));
+      acc.w += ((a.w + b.w) + (c.w + e.w)) + ((f.w + g.w) + (h.w + k.w));
+    }
     for (; r + 24 < r1; r += 32) {
       const float4 a = load(r), b = load(r + 8), c = load(r + 16), e = load(r + 24);
       acc.x += (a.x + b.x) + (c.x + e.x); acc.y += (a.y + b.y) + (c.y + e.y);
