@@ -12,12 +12,15 @@
 // Batches ride in tensor-map dimensions 2 and 3 (inner / outer batch index), which is how the
 // per-head [q|k|v] column layout of the QKV projection is addressed in place.
 //
-// Persistent: one CTA per SM loops over 128 x BN output tiles (n fastest, so the A panel of a
-// row of tiles stays in L2).  6 warps: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
-// (one elected lane), warps 2-5 = epilogue (one TMEM lane quarter each).  The accumulator is
+// Persistent: one CTA per SM (or one CTA pair per SM pair, tcgen05 cta_group::2) loops over 128 x BN
+// (256 x BN) output tiles, n fastest, so the A panel of a row of tiles stays in L2.  Warp 0 = TMA
+// producer, warp 1 = TMEM owner + MMA issuer (one elected lane), then the epilogue warps: 8 in the
+// fast epilogue (two per TMEM lane quarter), 4 in the general one.  The accumulator is
 // double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the main loop of
-// tile i+1.  Split-K partials go to a workspace (also by TMA store) and are reduced in fixed
-// order by gemm.cu (deterministic).
+// tile i+1.  Split-K partials go to a workspace (also by TMA store) and are added in fixed order by
+// gemm.cu's reduce kernel or directly by the consumer (Adam), deterministically either way.
+// This file is the host side: tile / pair / split-K choice, tensor maps, dispatch.  The kernel is
+// in gemm_tc_kernel.cuh, instantiated per tile width in gemm_tc_bn*.cu.
 #include "gemm_tc_kernel.cuh"
 
 namespace npt {
