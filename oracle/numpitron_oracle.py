@@ -530,3 +530,54 @@ def draw_batch(data: np.ndarray, rng: np.random.Generator, batch: int, seq_len: 
     start = rng.integers(0, len(data) - 1 - seq_len, size=batch)[:, None]
     rng_ = np.arange(seq_len)
     return data[start + rng_], data[start + 1 + rng_]
+
+
+# ---------------------------------------------------------------------------------------------------
+# checkpoint layout, sampling (test infrastructure like everything in this file)
+# ---------------------------------------------------------------------------------------------------
+def full_parameters_from_checkpoint(state: dict) -> dict:
+    """Map the reference's checkpoint tree (train_shakespeare.py:30-41: model.to_dict() of the gathered
+    model, nn/model.py:42-44, nn/core.py:96-99) onto the flat keys of `build_full_parameters`."""
+    layers = state["model_parameters"]["layers"]
+    P = {"embedding": layers["input_embedding"]["parameters"]["embedding"]["data"]}
+    i = 0
+    while f"block_{i}" in layers:
+        blk, pre = layers[f"block_{i}"]["layers"], f"block_{i}."
+        att, mlp = blk["attention"]["layers"], blk["mlp"]["layers"]
+        P[pre + "norm1.weight"] = blk["norm1"]["parameters"]["weight"]["data"]
+        P[pre + "norm1.bias"] = blk["norm1"]["parameters"]["bias"]["data"]
+        P[pre + "qkv.weight"] = att["qkv_projection"]["parameters"]["weight"]["data"]
+        P[pre + "out.weight"] = att["out_projection"]["parameters"]["weight"]["data"]
+        P[pre + "norm2.weight"] = blk["norm2"]["parameters"]["weight"]["data"]
+        P[pre + "norm2.bias"] = blk["norm2"]["parameters"]["bias"]["data"]
+        P[pre + "col.weight"] = mlp["column_linear"]["parameters"]["weight"]["data"]
+        P[pre + "col.bias"] = mlp["column_linear"]["parameters"]["bias"]["data"]
+        P[pre + "row.weight"] = mlp["row_linear"]["parameters"]["weight"]["data"]
+        P[pre + "row.bias"] = mlp["row_linear"]["parameters"]["bias"]["data"]
+        i += 1
+    return P
+
+
+def basic_sample(logits_last: np.ndarray, temperature: float, rng: np.random.Generator) -> int:
+    """sample_shakespeare.py:13-25 on the gathered last-position logits: softmax of
+    (logits / temperature) in float64, one multinomial draw, arg-max of the one-hot."""
+    probabilities = softmax((logits_last.astype(F32) / temperature).astype(np.float64))
+    return int(rng.multinomial(1, probabilities).argmax())
+
+
+def greedy_sample(logits_last: np.ndarray) -> int:
+    """sample_shakespeare.py:28-49 with the vocabulary shards already concatenated."""
+    return int(logits_last.argmax())
+
+
+def generate(model: "OracleTransformer", tokens, num_samples: int, temperature, rng) -> list:
+    """The loop of sample_shakespeare.py:67-75 (sliding context window, full forward per token)."""
+    tokens, out = list(tokens), []
+    for _ in range(num_samples):
+        tokens = tokens[-model.S:]
+        logits, _ = model._forward_replica(model.ranks[0], np.asarray([tokens], dtype=np.uint16))
+        last = np.concatenate([l[0, -1, :] for l in logits])   # all_gather over the TP group
+        nxt = greedy_sample(last) if temperature is None else basic_sample(last, temperature, rng)
+        tokens.append(nxt)
+        out.append(nxt)
+    return out

@@ -170,3 +170,33 @@ def test_reference_checkpoint_fixture_layout():
     assert list(op) == ["parameters", "timestep", "learning_rate", "beta1", "beta2", "eps"]
     m = op["parameters"]["block_0"]["norm1"]["weight"]["parameters"]["momentum"]
     assert m["data"].dtype == np.float32 and m["data"].shape == (32,)
+
+
+def test_oracle_loader_restatement_matches_reference_loader():
+    """O.draw_batch (data/loader.py:48-54 restated) reproduces the batches the reference's own DataLoader
+    yielded (tests/golden/loader_tp1.npz), from the same token stream and generator seed."""
+    with np.load(GOLDEN / "loader_tp1.npz") as z:
+        G = {k: z[k] for k in z.files}
+    data = np.random.default_rng(1234).integers(0, 17, 5000).astype(np.uint16)   # make_golden.LOADER_TOKENS
+    rng = np.random.default_rng(5)
+    for i in range(6):
+        x, y = O.draw_batch(data, rng, 4, 16)
+        np.testing.assert_array_equal(x, G[f"x{i}"])
+        np.testing.assert_array_equal(y, G[f"y{i}"])
+    assert len(data) // (16 * 4) == int(G["batches_per_epoch"])
+
+
+@pytest.mark.parametrize("tp", [1, 2])
+def test_oracle_sampling_from_reference_checkpoint(tp):
+    """The oracle, loaded from the checkpoint the reference wrote (tiny_checkpoint.npy), generates the
+    reference's own token sequences (sample_tp1.npz) — greedy and multinomial at two temperatures — also
+    when its vocabulary and weights are sharded over an emulated tp = 2 world."""
+    state = np.load(GOLDEN / "tiny_checkpoint.npy", allow_pickle=True)[()]
+    with np.load(GOLDEN / "sample_tp1.npz") as z:
+        G = {k: z[k] for k in z.files}
+    s = state["model_parameters"]["settings"]
+    model = O.OracleTransformer(s["d_model"], s["n_heads"], s["n_layers"], s["vocab_size"], s["seq_len"], tp=tp,
+                                full_params=O.full_parameters_from_checkpoint(state))
+    assert O.generate(model, [3], 24, None, None) == G["greedy"].tolist()
+    for name, temp in (("basic_t1", 1.0), ("basic_t40", 40.0)):
+        assert O.generate(model, [3], 24, temp, np.random.default_rng(42)) == G[name].tolist(), name
