@@ -565,9 +565,16 @@ def basic_sample(logits_last: np.ndarray, temperature: float, rng: np.random.Gen
     return int(rng.multinomial(1, probabilities).argmax())
 
 
-def greedy_sample(logits_last: np.ndarray) -> int:
-    """sample_shakespeare.py:28-49 with the vocabulary shards already concatenated."""
-    return int(logits_last.argmax())
+def greedy_sample(logit_shards) -> int:
+    """sample_shakespeare.py:28-49 over the per-rank vocabulary shards of the last position: every rank
+    reports (max value, arg-max + tp_rank * len(its shard)); the index of the rank with the largest value
+    wins.  The offset uses the rank's OWN shard length (:37), so with an uneven vocabulary split
+    (17 -> 9 + 8) an arg-max in a later shard comes out shifted — reproduced, like the other quirks."""
+    if isinstance(logit_shards, np.ndarray):
+        logit_shards = [logit_shards]
+    values = [float(s.max()) for s in logit_shards]
+    indices = [int(s.argmax()) + r * len(s) for r, s in enumerate(logit_shards)]
+    return int(np.float32(indices[int(np.argmax(values))]))
 
 
 def generate(model: "OracleTransformer", tokens, num_samples: int, temperature, rng) -> list:
@@ -576,8 +583,9 @@ def generate(model: "OracleTransformer", tokens, num_samples: int, temperature, 
     for _ in range(num_samples):
         tokens = tokens[-model.S:]
         logits, _ = model._forward_replica(model.ranks[0], np.asarray([tokens], dtype=np.uint16))
-        last = np.concatenate([l[0, -1, :] for l in logits])   # all_gather over the TP group
-        nxt = greedy_sample(last) if temperature is None else basic_sample(last, temperature, rng)
+        shards = [l[0, -1, :] for l in logits]
+        last = np.concatenate(shards)                          # all_gather over the TP group
+        nxt = greedy_sample(shards) if temperature is None else basic_sample(last, temperature, rng)
         tokens.append(nxt)
         out.append(nxt)
     return out

@@ -81,6 +81,19 @@ def main(tp, dp):
     gathered[npdist.data_parallel_rank()] = mine
     npdist.all_reduce(gathered, group=npdist.data_parallel_group())
     np.testing.assert_array_equal(gathered.reshape(x.shape), x.astype(np.float32))
+
+    # samplers across the tensor-parallel group (sample_shakespeare.py:13-49): each rank holds its shard of
+    # the last position's logits; the temperature sampler all-gathers them, the greedy one all-reduces
+    # (value, index) pairs — including the reference's index offset by the rank's OWN shard length
+    from numpitron_b200.sample import basic_sample, greedy_sample
+
+    npdist.init(tp_size=tp, dp_size=dp)
+    for seed in range(6):
+        full_logits = (np.random.default_rng(100 + seed).standard_normal(17) * 3).astype(np.float32)
+        shards = np.array_split(full_logits, tp)
+        local = shards[tr][None, None, :]
+        assert basic_sample(local, 0.7, np.random.default_rng(11), 17) == O.basic_sample(full_logits, 0.7, np.random.default_rng(11))
+        assert greedy_sample(local) == O.greedy_sample(shards)
     print(f"rank {rank} ok", flush=True)
 
 
