@@ -94,6 +94,35 @@ def main(tp, dp):
         local = shards[tr][None, None, :]
         assert basic_sample(local, 0.7, np.random.default_rng(11), 17) == O.basic_sample(full_logits, 0.7, np.random.default_rng(11))
         assert greedy_sample(local) == O.greedy_sample(shards)
+
+    # checkpoint round trip under tensor parallelism (train_shakespeare.py:30-41,87-93): gather, write the
+    # full tree, scatter again; the file holds the FULL parameters and Adam moments on every rank
+    import tempfile
+
+    from numpitron_b200.checkpoint import load_checkpoint, save_checkpoint
+
+    model.scatter()
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / f"ckpt_rank{rank}.npy"
+        save_checkpoint(model, opt, 3, 1.25, path)
+        assert model.is_scattered and tuple(model.block_0.attention.qkv_projection.weight.data.shape) == (32, 96 // tp)
+        state = np.load(path, allow_pickle=True)[()]
+        assert state["epoch"] == 3 and state["validation_loss"] == 1.25
+        blk = state["model_parameters"]["layers"]["block_0"]["layers"]
+        np.testing.assert_array_equal(blk["attention"]["layers"]["qkv_projection"]["parameters"]["weight"]["data"],
+                                      full["block_0.qkv.weight"])
+        np.testing.assert_array_equal(blk["mlp"]["layers"]["row_linear"]["parameters"]["weight"]["data"],
+                                      full["block_0.row.weight"])
+        np.testing.assert_array_equal(O.full_parameters_from_checkpoint(state)["embedding"], full["embedding"])
+        mom = state["optimizer_parameters"]["parameters"]["block_0"]["mlp"]["column_linear"]["weight"]["parameters"]["momentum"]
+        assert mom["data"].shape == (32, 128) and mom["shard_axis"] == 1
+        t2, o2, epoch, vloss = load_checkpoint(path)
+        assert epoch == 3 and vloss == 1.25 and not t2.is_scattered
+        np.testing.assert_array_equal(t2.block_1.mlp.column_linear.weight.data.numpy(), full["block_1.col.weight"])
+        t2.scatter()
+        o2.scatter()
+        np.testing.assert_array_equal(t2.block_1.mlp.column_linear.weight.data.numpy(),
+                                      O.shard(full["block_1.col.weight"], tp, tr, 1))
     print(f"rank {rank} ok", flush=True)
 
 
