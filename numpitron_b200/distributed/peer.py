@@ -23,6 +23,7 @@ NUMPITRON_TP_PEER=0 disables this and keeps the NCCL all-reduces.
 from __future__ import annotations
 
 import os
+import sys
 
 import torch
 
@@ -84,7 +85,8 @@ def exchange(shape, dtype=torch.bfloat16):
             _state["px"] = PeerExchange(tensor_parallel_group().pg, n * torch.empty((), dtype=dtype).element_size())
         except Exception as e:  # no P2P / symmetric memory on this system: keep the NCCL all-reduces
             _state["failed"] = True
-            print(f"[numpitron_b200] peer exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce", flush=True)
+            print(f"[numpitron_b200] peer exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce",
+                  file=sys.stderr, flush=True)   # stderr: bench.py's stdout is one JSON line
             return None
     return _state["px"]
 
