@@ -67,7 +67,14 @@ class DataLoader:
     def iter_epoch(self):
         """One pass over the dataset: `batches_per_epoch + 1` batches, like the reference's
         `while batch_idx <= self.batches_per_epoch` (loader.py:47)."""
-        batch_idx = 0
-        while batch_idx <= self.batches_per_epoch:
-            yield self.next_batch()
-            batch_idx += 1
+        def _iter_epoch():
+            batch_idx = 0
+            while batch_idx <= self.batches_per_epoch:
+                yield self.next_batch()
+                batch_idx += 1
+
+        # the reference returns the tqdm bar itself (loader.py:84-91): its training loop calls
+        # set_description() / refresh() on it (train_shakespeare.py:103-106)
+        import tqdm
+
+        return tqdm.tqdm(_iter_epoch(), leave=False, total=self.batches_per_epoch, disable=npdist.world_rank() != 0)

@@ -115,40 +115,51 @@ def _need(group, what):
     return group
 
 
+def _default_init() -> ParallelState:
+    """The reference initialises the groups as a side effect of importing nn/transformer.py
+    (`npdist.init(tp_size=npdist.world_size())`, nn/transformer.py:15), so its layers can be
+    built without an explicit init().  Same default here, but lazily — on the first use of a tensor / data /
+    pipeline parallel accessor — so that importing the package never opens a process group."""
+    st = _state()
+    if st.tensor_parallel_group is None:
+        init(tp_size=world_size())
+    return st
+
+
 def tensor_parallel_size() -> int:
-    return _need(_state().tensor_parallel_group, "Tensor Parallel").Get_size()
+    return _need(_default_init().tensor_parallel_group, "Tensor Parallel").Get_size()
 
 
 def tensor_parallel_rank() -> int:
-    return _need(_state().tensor_parallel_group, "Tensor Parallel").Get_rank()
+    return _need(_default_init().tensor_parallel_group, "Tensor Parallel").Get_rank()
 
 
 def tensor_parallel_group() -> Comm:
-    return _need(_state().tensor_parallel_group, "Tensor Parallel")
+    return _need(_default_init().tensor_parallel_group, "Tensor Parallel")
 
 
 def pipeline_parallel_size() -> int:
-    return _need(_state().pipeline_parallel_group, "Pipeline Parallel").Get_size()
+    return _need(_default_init().pipeline_parallel_group, "Pipeline Parallel").Get_size()
 
 
 def pipeline_parallel_rank() -> int:
-    return _need(_state().pipeline_parallel_group, "Pipeline Parallel").Get_rank()
+    return _need(_default_init().pipeline_parallel_group, "Pipeline Parallel").Get_rank()
 
 
 def pipeline_parallel_group() -> Comm:
-    return _need(_state().pipeline_parallel_group, "Pipeline Parallel")
+    return _need(_default_init().pipeline_parallel_group, "Pipeline Parallel")
 
 
 def data_parallel_size() -> int:
-    return _need(_state().data_parallel_group, "Data Parallel").Get_size()
+    return _need(_default_init().data_parallel_group, "Data Parallel").Get_size()
 
 
 def data_parallel_rank() -> int:
-    return _need(_state().data_parallel_group, "Data Parallel").Get_rank()
+    return _need(_default_init().data_parallel_group, "Data Parallel").Get_rank()
 
 
 def data_parallel_group() -> Comm:
-    return _need(_state().data_parallel_group, "Data Parallel")
+    return _need(_default_init().data_parallel_group, "Data Parallel")
 
 
 def add_group(all_groups_ranks) -> Comm | None:
@@ -187,4 +198,4 @@ def init(tp_size: int = 1, pp_size: int = 1, dp_size: int = 1) -> None:
     st.model_parallel_group = add_group([ranks[:, dp_rank, :].reshape(-1) for dp_rank in range(dp_size)])
 
 
-from .collectives import all_gather, all_reduce, all_reduce_async, broadcast, scatter  # noqa: E402,F401
+from .collectives import all_gather, all_reduce, all_reduce_async, all_reduce_bucket_async, broadcast, scatter  # noqa: E402,F401

@@ -68,6 +68,25 @@ def all_reduce_async(tensor: torch.Tensor, op: str = "sum", group=None):
     return work
 
 
+def all_reduce_bucket_async(tensors, op: str = "sum", group=None):
+    """One bucket = one coalesced all-reduce of several device buffers (a single ncclGroup: one launch, not one
+    per tensor), started asynchronously; returns a handle with `.wait()`.  Used by the labelled non-reference
+    data-parallel mode `dp_sync="all"` (nn/transformer.py): one bucket per TransformerBlock, issued as soon as
+    the block's backward is enqueued, so it overlaps the backward of the blocks below it."""
+    group = group or _default_group()
+    tensors = [t for t in tensors if t is not None]
+    if group.Get_size() == 1 or not tensors:
+        return _Done()
+    from torch.distributed.distributed_c10d import _coalescing_manager
+
+    with _coalescing_manager(group=group.pg, async_ops=True) as cm:
+        for t in tensors:
+            dist.all_reduce(t, op=_OPS[op], group=group.pg)
+    for t in tensors:
+        rt.drop_bf16(t)
+    return cm
+
+
 def broadcast(tensor, src: int = 0, group=None) -> None:
     group = group or _default_group()
     if group.Get_size() == 1:

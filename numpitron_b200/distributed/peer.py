@@ -72,23 +72,47 @@ def enabled() -> bool:
 
 
 def exchange(shape, dtype=torch.bfloat16):
-    """The process-wide PeerExchange (created on first use), or None when unavailable."""
+    """The process-wide PeerExchange, or None when unavailable.  Created on first use and re-created
+    (collectively: every tensor-parallel rank runs the same layer code on the same shapes, so all of them
+    get here in the same call) when a tensor larger than its slots comes along — a bigger batch, a
+    validation shape.  Whether the exchange is usable is agreed on by the whole group: a rank whose
+    allocation or rendezvous failed must not fall back to NCCL alone while its peer waits at the barrier."""
     if not enabled():
         return None
-    if _state["px"] is None:
-        from . import tensor_parallel_group
+    n = 1
+    for s in shape:
+        n *= int(s)
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    px = _state["px"]
+    if px is not None and nbytes <= px.slot_bytes:
+        return px
+    import torch.distributed as dist
 
-        n = 1
-        for s in shape:
-            n *= int(s)
-        try:
-            _state["px"] = PeerExchange(tensor_parallel_group().pg, n * torch.empty((), dtype=dtype).element_size())
-        except Exception as e:  # no P2P / symmetric memory on this system: keep the NCCL all-reduces
-            _state["failed"] = True
-            print(f"[numpitron_b200] peer exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce",
-                  file=sys.stderr, flush=True)   # stderr: bench.py's stdout is one JSON line
-            return None
-    return _state["px"]
+    from . import tensor_parallel_group
+
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("peer exchange would have to grow during CUDA-graph capture; run a warm-up step first")
+    pg = tensor_parallel_group().pg
+    new, err = None, None
+    try:
+        torch.cuda.synchronize()   # nothing still reads the slots that are about to be released
+        new = PeerExchange(pg, nbytes)
+    except Exception as e:  # no P2P / symmetric memory on this system
+        err = e
+    ok = torch.tensor([0 if new is None else 1], dtype=torch.int32, device=rt.device())
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=pg)
+    if int(ok.item()) == 0:
+        _state["failed"], _state["px"] = True, None
+        print(f"[numpitron_b200] peer exchange unavailable on at least one rank ({type(err).__name__ if err else 'peer'}: "
+              f"{err}); using NCCL all-reduce", file=sys.stderr, flush=True)   # stderr: bench.py's stdout is one JSON line
+        return None
+    _state["px"] = new
+    return new
+
+
+def active() -> bool:
+    """True when the tensor-parallel exchange really runs through peer memory (an exchange exists)."""
+    return _state["px"] is not None
 
 
 def reset():

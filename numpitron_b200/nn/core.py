@@ -51,6 +51,21 @@ def weight_init_fn(name: str = "default", rng: Generator | None = None, scale: f
             "scaled_normal": scaled_normal, "init_for_testing": init_for_testing}[name]
 
 
+# Bumped whenever a parameter's STORAGE is replaced (scatter / all_gather / from_dict / a new `data`
+# through update_parameter).  A captured CUDA graph holds raw device pointers of every parameter, Adam
+# moment and bf16 shadow: train.GraphedTrainStep compares this counter before every replay and re-captures
+# when it moved (Adam.step updates in place and does not count).
+_STORAGE_GENERATION = [0]
+
+
+def storage_generation() -> int:
+    return _STORAGE_GENERATION[0]
+
+
+def bump_storage_generation() -> None:
+    _STORAGE_GENERATION[0] += 1
+
+
 @dataclass(frozen=True)
 class Parameter:
     data: torch.Tensor
@@ -115,6 +130,7 @@ class Layer:
         setattr(self, name, Parameter(data=data, gradient=None, shard_axis=shard_axis))
         self.parameters[name] = getattr(self, name)
         self._shadows.pop(name, None)
+        bump_storage_generation()
 
     def add_setting(self, name, value):
         setattr(self, name, value)
@@ -131,6 +147,7 @@ class Layer:
                 updates[key] = _to_f32_tensor(updates[key])
         if "data" in updates and updates["data"] is not current_parameter.data:
             self._shadows.pop(name, None)
+            bump_storage_generation()
         setattr(self, name, replace(current_parameter, **updates))
         self.parameters[name] = getattr(self, name)
 

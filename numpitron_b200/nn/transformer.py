@@ -4,9 +4,24 @@ from __future__ import annotations
 from functools import partial
 
 from .. import distributed as npdist
+from .. import runtime as rt
 from .embedding import InputEmbedding, OutputEmbedding, PositionalEncoding
 from .model import Model
 from .transformer_block import TransformerBlock
+
+
+def set_dp_sync(mode: str) -> None:
+    rt.set_dp_sync(mode)
+
+
+def _gradients_below(layer):
+    """Every gradient held by the (nested) layers of a Model, in definition order."""
+    out = []
+    for sub in layer.layers.values():
+        if isinstance(sub, Model):
+            out += _gradients_below(sub)
+        out += [p.gradient for p in sub.parameters.values() if p.gradient is not None]
+    return out
 
 
 class Transformer(Model):
@@ -35,15 +50,27 @@ class Transformer(Model):
     def backward(self, d_out):
         """Reverse pass; after each TOP-LEVEL layer its own parameters are all-reduced (SUM) over the
         data-parallel group — which in practice is only the tied embedding gradient, because a
-        TransformerBlock's own `parameters` dict is empty (reference: transformer.py:48-59, Q11)."""
+        TransformerBlock's own `parameters` dict is empty (reference: transformer.py:48-59, Q11).
+
+        `rt.set_dp_sync("all")` (non-reference): the gradients of every parameter below a
+        block are summed over the group as well — one coalesced bucket per block, started asynchronously as
+        soon as the block's backward is enqueued, so the transfers run under the backward pass of the blocks
+        below; all buckets are waited for before the optimizer may run."""
         blocks = [layer for layer in self.layers.values() if isinstance(layer, TransformerBlock)]
         if blocks:
             blocks[0].input_grad_f32 = True  # its dX goes to the embedding layers (fp32 readers)
+        dp = npdist.data_parallel_size() > 1
+        sync_all = dp and rt.dp_sync() == "all"
+        pending = []
         for layer in list(self.layers.values())[::-1]:
             d_out = layer.backward(d_out)
-            if npdist.data_parallel_size() > 1:
+            if dp:
+                if sync_all and isinstance(layer, Model):
+                    pending.append(npdist.all_reduce_bucket_async(_gradients_below(layer), group=npdist.data_parallel_group()))
                 for parameter in layer.parameters.values():
                     npdist.all_reduce(parameter.gradient, group=npdist.data_parallel_group())
+        for handle in pending:
+            handle.wait()
         return d_out
 
     @classmethod

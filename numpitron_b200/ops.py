@@ -24,6 +24,37 @@ def _p(t, off=0):
     return rt.ptr(t, off)
 
 
+# ---- per-launch timing (bench.py's roofline legs, benchmarks/microbench.py) -------------------------------
+PROFILE = None   # set to a list: every op below then appends dict(name, bound, work, events) per C-ABI call
+
+
+def _nbytes(*tensors) -> int:
+    return sum(t.numel() * t.element_size() for t in tensors if t is not None)
+
+
+class _timed:
+    """CUDA events around one C-ABI call, on the launching stream.  `work` = algorithmic bytes (bound "hbm")
+    or FLOPs (bound "tensor") of the call."""
+
+    __slots__ = ("name", "bound", "work", "info", "e0")
+
+    def __init__(self, name: str, bound: str, work: float, **info):
+        self.name, self.bound, self.work, self.info = name, bound, work, info
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append(dict(name=self.name, bound=self.bound, work=float(self.work), events=(self.e0, e1), **self.info))
+        return False
+
+
 def set_sm_margin(sms: int) -> None:
     """Leave `sms` SMs out of the persistent GEMM grids (room for an in-flight NCCL collective)."""
     check(_lib_().npt_set_sm_margin(int(sms)), "npt_set_sm_margin")
@@ -84,20 +115,10 @@ def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_of
         else:
             ws = rt.workspace(need)
             g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
-    if GEMM_PROFILE is None:
+    with _timed("gemm", "tensor", 2.0 * M * N * K * batch, M=M, N=N, K=K, batch=batch,
+                trans=(int(trans_a), int(trans_b)), mode=mode, splitk=bool(need)):
         check(lib.npt_gemm(C.byref(g), rt.stream()), "npt_gemm")
-        return partials
-    # bench.py's roofline leg: CUDA events around this launch, on the launching stream
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    check(lib.npt_gemm(C.byref(g), rt.stream()), "npt_gemm")
-    e1.record()
-    GEMM_PROFILE.append(dict(events=(e0, e1), flops=2.0 * M * N * K * batch, M=M, N=N, K=K, batch=batch,
-                             trans=(int(trans_a), int(trans_b)), mode=mode, splitk=bool(need)))
     return partials
-
-
-GEMM_PROFILE = None  # set to a list to collect per-launch timings
 
 
 def cast_bf16(t: torch.Tensor, pad_cols: bool = False) -> torch.Tensor:
@@ -128,9 +149,10 @@ def layernorm_fwd(x, gamma, beta, eps, residual=None, want_bf16=False, x_peer: i
     yb = rt.empty(x.shape, _BF16) if want_bf16 else None
     mean, var = rt.empty((rows,)), rt.empty((rows,))
     x_sum = rt.empty(x.shape, _BF16) if x_peer else None
-    check(lib.npt_layernorm_fwd_v2(_p(x), int(x.dtype == _BF16), x_peer or None, _p(x_sum), _p(gamma), _p(beta),
-                                   _p(residual), _p(y), _p(yb), _p(mean), _p(var), rows, d, eps, rt.stream()),
-          "npt_layernorm_fwd_v2")
+    with _timed("layernorm_fwd", "hbm", _nbytes(x, residual, y, yb, mean, var, x_sum) + (_nbytes(x) if x_peer else 0)):
+        check(lib.npt_layernorm_fwd_v2(_p(x), int(x.dtype == _BF16), x_peer or None, _p(x_sum), _p(gamma), _p(beta),
+                                       _p(residual), _p(y), _p(yb), _p(mean), _p(var), rows, d, eps, rt.stream()),
+              "npt_layernorm_fwd_v2")
     if yb is not None:
         rt.attach_bf16(y, yb)
     if x_peer:
@@ -159,9 +181,10 @@ def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False, bf16_only=False
     if in_bf16 and dy.dtype != _BF16:
         dy = cast_bf16(dy)
     assert not dy_peer or in_bf16
-    check(lib.npt_layernorm_bwd_v2(_p(x), _p(dy), int(in_bf16), dy_peer or None, _p(gamma), _p(mean), _p(var), _p(dx), _p(dxb),
-                                   _p(dgamma), _p(dbeta), _p(colsum_out), rows, d, eps, ws.data_ptr(), ws.numel(),
-                                   rt.stream()), "npt_layernorm_bwd_v2")
+    with _timed("layernorm_bwd", "hbm", _nbytes(x, dy, dx, dxb, mean, var) + (_nbytes(dy) if dy_peer else 0)):
+        check(lib.npt_layernorm_bwd_v2(_p(x), _p(dy), int(in_bf16), dy_peer or None, _p(gamma), _p(mean), _p(var), _p(dx), _p(dxb),
+                                       _p(dgamma), _p(dbeta), _p(colsum_out), rows, d, eps, ws.data_ptr(), ws.numel(),
+                                       rt.stream()), "npt_layernorm_bwd_v2")
     out = dxb if bf16_only else dx
     if not bf16_only and dxb is not None:
         rt.attach_bf16(dx, dxb)
@@ -197,8 +220,9 @@ def colsum(x2d_rows: int, cols: int, x: torch.Tensor, ld: int | None = None) -> 
     out = rt.empty((cols,))
     need = lib.npt_colsum_workspace_bytes(x2d_rows, cols)
     ws = rt.workspace(need)
-    check(lib.npt_colsum(_p(x), int(x.dtype == _BF16), ld, _p(out), x2d_rows, cols, ws.data_ptr(), ws.numel(),
-                         rt.stream()), "npt_colsum")
+    with _timed("colsum", "hbm", x2d_rows * cols * x.element_size()):
+        check(lib.npt_colsum(_p(x), int(x.dtype == _BF16), ld, _p(out), x2d_rows, cols, ws.data_ptr(), ws.numel(),
+                             rt.stream()), "npt_colsum")
     return out
 
 
@@ -209,7 +233,8 @@ def softmax_causal_fwd(scores, divisor, want_bf16=False, bf16_only=False):
     n_mats = scores.numel() // (S * S)
     p = None if bf16_only else rt.empty(scores.shape)
     pb = rt.empty(scores.shape, _BF16) if (want_bf16 or bf16_only) else None
-    check(lib.npt_softmax_causal_fwd(_p(scores), _p(p), _p(pb), n_mats, S, divisor, rt.stream()), "npt_softmax_causal_fwd")
+    with _timed("softmax_causal_fwd", "hbm", _nbytes(scores) // 2 + (_nbytes(p, pb))):
+        check(lib.npt_softmax_causal_fwd(_p(scores), _p(p), _p(pb), n_mats, S, divisor, rt.stream()), "npt_softmax_causal_fwd")
     if bf16_only:
         return pb
     if pb is not None:
@@ -224,8 +249,9 @@ def softmax_causal_bwd(p, dp, divisor, want_bf16=False, bf16_only=False):
     n_mats = p.numel() // (S * S)
     ds = None if bf16_only else rt.empty(p.shape)
     dsb = rt.empty(p.shape, _BF16) if (want_bf16 or bf16_only) else None
-    check(lib.npt_softmax_causal_bwd(_p(p), int(p.dtype == _BF16), _p(dp), _p(ds), _p(dsb), n_mats, S, divisor,
-                                     rt.stream()), "npt_softmax_causal_bwd")
+    with _timed("softmax_causal_bwd", "hbm", (_nbytes(p, dp)) // 2 + _nbytes(ds, dsb)):
+        check(lib.npt_softmax_causal_bwd(_p(p), int(p.dtype == _BF16), _p(dp), _p(ds), _p(dsb), n_mats, S, divisor,
+                                         rt.stream()), "npt_softmax_causal_bwd")
     if bf16_only:
         return dsb
     if dsb is not None:
@@ -244,7 +270,8 @@ def attention_fwd(qkv_b, B, S, h, Dh, divisor):
     assert qkv_b.dtype == _BF16 and qkv_b.is_contiguous()
     out = rt.empty((B, S, h * Dh), _BF16)
     lse = rt.empty((B, h, S))
-    check(lib.npt_attention_fwd(_p(qkv_b), _p(out), _p(lse), B, S, h, Dh, divisor, rt.stream()), "npt_attention_fwd")
+    with _timed("attention_fwd", "tensor", 2.0 * B * h * S * S * Dh):
+        check(lib.npt_attention_fwd(_p(qkv_b), _p(out), _p(lse), B, S, h, Dh, divisor, rt.stream()), "npt_attention_fwd")
     return out, lse
 
 
@@ -255,8 +282,9 @@ def attention_bwd(qkv_b, out_b, d_out_b, lse, B, S, h, Dh, divisor):
     dqkv = rt.empty((B, S, h * 3 * Dh), _BF16)
     need = lib.npt_attention_bwd_workspace_bytes(B, S, h)
     ws = rt.workspace(need)
-    check(lib.npt_attention_bwd(_p(qkv_b), _p(out_b), _p(d_out_b), _p(lse), _p(dqkv), B, S, h, Dh, divisor,
-                                ws.data_ptr(), ws.numel(), rt.stream()), "npt_attention_bwd")
+    with _timed("attention_bwd", "tensor", 5.0 * B * h * S * S * Dh):
+        check(lib.npt_attention_bwd(_p(qkv_b), _p(out_b), _p(d_out_b), _p(lse), _p(dqkv), B, S, h, Dh, divisor,
+                                    ws.data_ptr(), ws.numel(), rt.stream()), "npt_attention_bwd")
     return dqkv
 
 
@@ -268,8 +296,9 @@ def embedding_gather(tokens, E, pos, S, chunk_start, chunk_end, masked, want_bf1
     T = tokens.numel()
     out = rt.empty((*tokens.shape, d))
     ob = rt.empty((*tokens.shape, d), _BF16) if want_bf16 else None
-    check(lib.npt_embedding_gather(_p(tokens), _p(E), ldE, _p(pos), _p(out), _p(ob), T, S, d, chunk_start, chunk_end,
-                                   int(masked), rt.stream()), "npt_embedding_gather")
+    with _timed("embedding_gather", "hbm", _nbytes(tokens, out, ob) + T * d * 4):
+        check(lib.npt_embedding_gather(_p(tokens), _p(E), ldE, _p(pos), _p(out), _p(ob), T, S, d, chunk_start, chunk_end,
+                                       int(masked), rt.stream()), "npt_embedding_gather")
     if ob is not None:
         rt.attach_bf16(out, ob)
     return out
@@ -282,7 +311,8 @@ def add_pos(x, pos, S, want_bf16=False):
     T = x.numel() // d
     out = rt.empty(x.shape)
     ob = rt.empty(x.shape, _BF16) if want_bf16 else None
-    check(lib.npt_add_pos(_p(x), _p(pos), _p(out), _p(ob), T, S, d, rt.stream()), "npt_add_pos")
+    with _timed("add_pos", "hbm", _nbytes(x, out, ob)):
+        check(lib.npt_add_pos(_p(x), _p(pos), _p(out), _p(ob), T, S, d, rt.stream()), "npt_add_pos")
     if ob is not None:
         rt.attach_bf16(out, ob)
     return out
@@ -296,8 +326,9 @@ def embedding_scatter_add(tokens, d_out, grad, chunk_start, chunk_end, masked):
     T = tokens.numel()
     need = lib.npt_embedding_scatter_add_workspace_bytes(T, V_local)
     ws = rt.workspace(need)
-    check(lib.npt_embedding_scatter_add(_p(tokens), _p(d_out), _p(grad), ldG, T, d, V_local, chunk_start, chunk_end,
-                                        int(masked), ws.data_ptr(), ws.numel(), rt.stream()), "npt_embedding_scatter_add")
+    with _timed("embedding_scatter_add", "hbm", _nbytes(tokens, d_out) + 2 * _nbytes(grad)):
+        check(lib.npt_embedding_scatter_add(_p(tokens), _p(d_out), _p(grad), ldG, T, d, V_local, chunk_start, chunk_end,
+                                            int(masked), ws.data_ptr(), ws.numel(), rt.stream()), "npt_embedding_scatter_add")
     return grad
 
 
@@ -310,8 +341,9 @@ def softmax_ce_fused(logits, labels, chunk_start, chunk_end, want_bf16=False):
     grad = rt.empty(logits.shape)
     ldgb = rt.pad8(V)
     gb = rt.empty((*logits.shape[:-1], ldgb), _BF16) if want_bf16 else None
-    check(lib.npt_softmax_ce_fused(_p(logits), V, _p(labels), _p(loss), _p(grad), V, _p(gb), ldgb, T, V, chunk_start,
-                                   chunk_end, rt.stream()), "npt_softmax_ce_fused")
+    with _timed("softmax_ce_fused", "hbm", _nbytes(logits, labels, loss, grad, gb)):
+        check(lib.npt_softmax_ce_fused(_p(logits), V, _p(labels), _p(loss), _p(grad), V, _p(gb), ldgb, T, V, chunk_start,
+                                       chunk_end, rt.stream()), "npt_softmax_ce_fused")
     if gb is not None:
         rt.attach_bf16(grad, gb)
     return loss, grad
@@ -322,7 +354,8 @@ def softmax_ce_stage1(logits):
     V = logits.shape[-1]
     T = logits.numel() // V
     rowmax = rt.empty((T,))
-    check(lib.npt_softmax_ce_stage1(_p(logits), V, _p(rowmax), T, V, rt.stream()), "npt_softmax_ce_stage1")
+    with _timed("softmax_ce_stage1", "hbm", _nbytes(logits, rowmax)):
+        check(lib.npt_softmax_ce_stage1(_p(logits), V, _p(rowmax), T, V, rt.stream()), "npt_softmax_ce_stage1")
     return rowmax
 
 
@@ -331,8 +364,9 @@ def softmax_ce_stage2(logits, labels, rowmax, chunk_start, chunk_end):
     V = logits.shape[-1]
     T = logits.numel() // V
     picked, sumexp = rt.empty((T,)), rt.empty((T,))
-    check(lib.npt_softmax_ce_stage2(_p(logits), V, _p(labels), _p(rowmax), _p(picked), _p(sumexp), T, V, chunk_start,
-                                    chunk_end, rt.stream()), "npt_softmax_ce_stage2")
+    with _timed("softmax_ce_stage2", "hbm", _nbytes(logits, labels, rowmax, picked, sumexp)):
+        check(lib.npt_softmax_ce_stage2(_p(logits), V, _p(labels), _p(rowmax), _p(picked), _p(sumexp), T, V, chunk_start,
+                                        chunk_end, rt.stream()), "npt_softmax_ce_stage2")
     return picked, sumexp
 
 
@@ -344,8 +378,9 @@ def softmax_ce_stage3(logits, labels, rowmax, picked, sumexp, chunk_start, chunk
     grad = rt.empty(logits.shape)
     ldgb = rt.pad8(V)
     gb = rt.empty((*logits.shape[:-1], ldgb), _BF16) if want_bf16 else None
-    check(lib.npt_softmax_ce_stage3(_p(logits), V, _p(labels), _p(rowmax), _p(picked), _p(sumexp), _p(loss), _p(grad), V,
-                                    _p(gb), ldgb, T, V, chunk_start, chunk_end, rt.stream()), "npt_softmax_ce_stage3")
+    with _timed("softmax_ce_stage3", "hbm", _nbytes(logits, labels, rowmax, picked, sumexp, loss, grad, gb)):
+        check(lib.npt_softmax_ce_stage3(_p(logits), V, _p(labels), _p(rowmax), _p(picked), _p(sumexp), _p(loss), _p(grad), V,
+                                        _p(gb), ldgb, T, V, chunk_start, chunk_end, rt.stream()), "npt_softmax_ce_stage3")
     if gb is not None:
         rt.attach_bf16(grad, gb)
     return loss, grad
@@ -405,15 +440,17 @@ class AdamTable:
         self.n = 0
         self.key = None
         self.keep = None
+        self.nbytes = 0
+        self.upload_done = None   # event recorded after the last upload, on the stream that issued it
 
     def fill(self, entries):
         """entries: list of (p, g, m, v, shadow_or_None).  Re-uploads only when a pointer changed."""
-        key = tuple((_p(p), _p(g), _p(m), _p(v), _p(sh)) for p, g, m, v, sh in entries)
+        key = tuple((_p(p), _p(g), _p(m), _p(v), _p(sh), getattr(g, "_npt_splits", 1), p.numel()) for p, g, m, v, sh in entries)
         if key == self.key:
             return
         assert len(entries) <= self.capacity
-        if self.key is not None and not torch.cuda.is_current_stream_capturing():
-            torch.cuda.current_stream().synchronize()  # an earlier upload may still be reading `pinned`
+        if self.upload_done is not None and not torch.cuda.is_current_stream_capturing():
+            self.upload_done.synchronize()  # the earlier upload (whatever stream issued it) has read `pinned`
         C.memset(self.host, 0, C.sizeof(self.host))
         for i, (p, g, m, v, sh) in enumerate(entries):
             t = self.host[i]
@@ -427,10 +464,18 @@ class AdamTable:
                 t.shadow_ld = sh.shape[-1]
         C.memmove(self.pinned.ptr, self.host, C.sizeof(self.host))
         self.pinned.to_device(self.dev)  # async memcpy node: safe under graph capture
+        if not torch.cuda.is_current_stream_capturing():
+            self.upload_done = torch.cuda.Event()
+            self.upload_done.record()
         self.n, self.key, self.keep = len(entries), key, entries
+        # algorithmic bytes of one step over this table: read p, g (every split-K partial), m, v; write p, m, v
+        # (+ the bf16 shadow) = 28 B / parameter for a plain gradient
+        self.nbytes = sum(p.numel() * (24 + 4 * getattr(g, "_npt_splits", 1) + (2 if sh is not None else 0))
+                          for p, g, m, v, sh in entries)
 
 
 def adam_step(table: AdamTable, lr, b1, omb1, b2, omb2, c1, c2, eps):
     lib = _lib_()
-    check(lib.npt_adam_step(table.dev.data_ptr(), table.host, table.n, lr, b1, omb1, b2, omb2, c1, c2, eps, rt.stream()),
-          "npt_adam_step")
+    with _timed("adam_step", "hbm", table.nbytes):
+        check(lib.npt_adam_step(table.dev.data_ptr(), table.host, table.n, lr, b1, omb1, b2, omb2, c1, c2, eps, rt.stream()),
+              "npt_adam_step")

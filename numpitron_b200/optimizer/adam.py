@@ -98,7 +98,10 @@ class Adam:
         reads it)."""
         import torch
 
-        key = tuple((rt.ptr(a), rt.ptr(b), rt.ptr(c), rt.ptr(d), rt.ptr(e)) for a, b, c, d, e in entries)
+        # the gradient may be a stack of split-K partials at the address an earlier plain gradient had: the
+        # split count and the element count are part of the identity of an entry
+        key = tuple((rt.ptr(a), rt.ptr(b), rt.ptr(c), rt.ptr(d), rt.ptr(e), getattr(b, "_npt_splits", 1), a.numel())
+                    for a, b, c, d, e in entries)
         cap = max(len(entries), self._count_parameters())
         capturing = torch.cuda.is_current_stream_capturing()
         if not capturing:
@@ -134,7 +137,7 @@ class Adam:
                 value.scatter()
             else:
                 self.scatter(value)
-        self._table = None
+        self._drop_tables()
 
     def all_gather(self, params: dict = None):
         if params is None:
@@ -144,7 +147,14 @@ class Adam:
                 value.all_gather()
             else:
                 self.all_gather(params=value)
+        self._drop_tables()
+
+    def _drop_tables(self):
+        """Parameter / moment storage was replaced: every pointer table is stale.  Captured graphs that
+        still reference one are invalidated through nn.core.storage_generation() (GraphedTrainStep
+        re-captures), so nothing keeps the old buffers alive."""
         self._table = None
+        self._tables = {}
 
     def to_dict(self):
         def _to_dict(params) -> dict:

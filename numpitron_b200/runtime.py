@@ -125,7 +125,24 @@ class deferred_wgrad:
 
 
 def defer_wgrad() -> bool:
-    return bool(_state.get("defer_wgrad", False))
+    # dp_sync="all" all-reduces every weight gradient over the data-parallel group: it needs the reduced
+    # gradient, not the stack of split-K partials
+    return bool(_state.get("defer_wgrad", False)) and _state.get("dp_sync", "reference") == "reference"
+
+
+# ---- data-parallel gradient synchronisation mode ---------------------------------------------------------
+def set_dp_sync(mode: str) -> None:
+    """"reference" (default): only the tied embedding gradient is all-reduced over the data-parallel group,
+    exactly what the reference does (nn/transformer.py:48-59, SURVEY Q11 — block weights diverge between
+    replicas).  "all": a labelled NON-reference mode — every gradient is summed over the group, one bucket
+    per TransformerBlock, overlapped with the backward pass of the blocks below."""
+    if mode not in ("reference", "all"):
+        raise ValueError(f"dp_sync must be 'reference' or 'all', got {mode!r}")
+    _state["dp_sync"] = mode
+
+
+def dp_sync() -> str:
+    return _state.get("dp_sync", "reference")
 
 
 def workspace(nbytes: int) -> torch.Tensor:

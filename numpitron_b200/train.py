@@ -8,7 +8,7 @@ import torch
 from . import _lib, ops
 from . import runtime as rt
 from .nn import softmax_cross_entropy
-from .nn.core import _host_to_device
+from .nn.core import _host_to_device, storage_generation
 
 
 def _tokens(a):
@@ -65,6 +65,7 @@ class GraphedTrainStep:
         self.stream = torch.cuda.Stream()
         # parameters / shadows were produced on the caller's stream: order the step stream after it
         self.stream.wait_stream(torch.cuda.current_stream())
+        self._generation = storage_generation()
 
     # -- bodies -----------------------------------------------------------------------------------
     def _compute(self):
@@ -80,7 +81,20 @@ class GraphedTrainStep:
         self._compute()
         self._loss_pin.from_device(self.loss_dev)
 
+    def _check_storage(self) -> None:
+        """The captured graphs hold raw pointers of every parameter, Adam moment and bf16 shadow.  When any
+        of that storage was replaced since the capture (checkpointing gathers and re-scatters the model and
+        the optimizer: train_shakespeare.py:30-41), the graphs would keep training the orphaned buffers —
+        drop them, run the eager warm-up steps again on the new storage and re-capture."""
+        gen = storage_generation()
+        if gen != self._generation:
+            self._generation = gen
+            self.graph = self.graph_resident = None
+            self._eager_steps = 0
+            self.stream.wait_stream(torch.cuda.current_stream())   # the new buffers were filled on the caller's stream
+
     def _warm(self, body) -> bool:
+        self._check_storage()
         if self._eager_steps < self.warmup:
             with torch.cuda.stream(self.stream):
                 body()
@@ -118,6 +132,12 @@ class GraphedTrainStep:
     def load_resident(self, x_dev: torch.Tensor, y_dev: torch.Tensor) -> None:
         """Device-to-device copy of a resident batch into the graph's token buffers (stream-ordered)."""
         lib = _lib.load()
+        # x_dev / y_dev were produced on the caller's stream (DataLoader.next_batch launches its gather there):
+        # the copies below must wait for it, and the caching allocator must not hand the source buffers to
+        # someone else while the step stream still reads them
+        self.stream.wait_stream(torch.cuda.current_stream())
+        x_dev.record_stream(self.stream)
+        y_dev.record_stream(self.stream)
         with torch.cuda.stream(self.stream):
             n = self.x_dev.numel() * 2
             ops.check(lib.npt_memcpy_async(self.x_dev.data_ptr(), x_dev.data_ptr(), n, 3, rt.stream()), "memcpy")

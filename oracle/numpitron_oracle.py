@@ -364,6 +364,10 @@ class OracleTransformer:
             d_model, n_heads, n_layers, vocab, rng)
         self.pos = positional_table(d_model, seq_len)
         self.h_local = n_heads // tp  # attention.py:37-41 — no divisibility check (Q5)
+        # test hooks: with keep=True every train_step leaves the per-rank logits (of the forward) and the
+        # per-rank gradients (as they reach Adam) in last_logits[dp_rank][tp_rank] / last_grads[...]
+        self.keep = False
+        self.last_logits, self.last_grads = [], []
         self.bounds = [vocab_chunk_bounds(vocab, tp, r) for r in range(tp)]
         self.ranks: list[list[RankState]] = []
         for dr in range(dp):
@@ -486,8 +490,11 @@ class OracleTransformer:
         """Forward + loss on the whole emulated world.  Returns per-replica (loss, ctx, dlogits)."""
         xs, ys = self.split_batch(x), self.split_batch(y)
         out = []
+        self.last_logits = []
         for row, xb, yb in zip(self.ranks, xs, ys):
             logits, ctx = self._forward_replica(row, xb, trace)
+            if self.keep:
+                self.last_logits.append(logits)
             if trace is not None:
                 trace["logits"] = [l.copy() for l in logits]
             loss, dl = softmax_cross_entropy_world(logits, yb.copy(), self.bounds)
@@ -510,6 +517,8 @@ class OracleTransformer:
                     self.ranks[dr][tr].grads["embedding"] = tot.copy()
         if trace is not None:
             trace["grads"] = {k: v.copy() for k, v in self.ranks[0][0].grads.items()}
+        if self.keep:
+            self.last_grads = [[dict(st.grads) for st in row] for row in self.ranks]
         for row in self.ranks:
             for st in row:
                 for name, g in st.grads.items():

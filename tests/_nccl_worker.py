@@ -86,7 +86,18 @@ def main(tp, dp, precision):
     torch.cuda.synchronize()
     print(f"rank {rank} ok", flush=True)
     sys.stdout.flush()
-    os._exit(0)  # skip NCCL teardown (it can block behind captured graphs); the work is verified
+    # orderly teardown: the captured graphs hold NCCL kernels and references into the symmetric-memory
+    # exchange — release them, quiesce the device, then leave the process group together
+    import gc
+
+    from numpitron_b200.distributed import peer
+
+    del g, model2, opt2, model, opt
+    peer.reset()
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -19,24 +19,19 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("tp,dp", [(2, 1), (2, 2)])
-def test_tiny_train_steps_vs_reference_world(tp, dp, precision):
-    world = tp * dp
-    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
+def _run_world(worker, args, world, timeout=150, extra_env=None):
+    """One process per GPU; fail fast: as soon as one rank dies the others are stuck in a collective -> kill them."""
     import time
 
-    def run_world():
+    def once():
         port = _free_port()
         procs = []
         for r in range(world):
             env = dict(os.environ, WORLD_SIZE=str(world), RANK=str(r), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
-                       MASTER_PORT=str(port))
-            procs.append(subprocess.Popen([sys.executable, str(WORKER), str(tp), str(dp), precision], env=env,
+                       MASTER_PORT=str(port), **(extra_env or {}))
+            procs.append(subprocess.Popen([sys.executable, str(worker), *map(str, args)], env=env,
                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-        # fail fast: as soon as one rank dies the others are stuck in a collective -> kill them
-        deadline = time.time() + 150
+        deadline = time.time() + timeout
         failed = None
         while time.time() < deadline:
             codes = [p.poll() for p in procs]
@@ -51,10 +46,54 @@ def test_tiny_train_steps_vs_reference_world(tp, dp, precision):
                 p.kill()
         return procs, [p.communicate()[0] for p in procs], failed
 
-    procs, outs, failed = run_world()
+    procs, outs, failed = once()
     if failed is not None and "EADDRINUSE" in outs[failed]:  # the probed rendezvous port was taken meanwhile
-        procs, outs, failed = run_world()
+        procs, outs, failed = once()
     assert failed is None, f"rank {failed} failed:\n{outs[failed][-3000:]}"
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} did not finish:\n{out[-3000:]}"
         assert f"rank {r} ok" in out
+    return outs
+
+
+def _need_gpus(world):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tp,dp", [(2, 1), (2, 2)])
+def test_tiny_train_steps_vs_reference_world(tp, dp, precision):
+    _need_gpus(tp * dp)
+    _run_world(WORKER, [tp, dp, precision], tp * dp)
+
+
+CONFIG_WORKER = Path(__file__).resolve().parent / "_nccl_config_worker.py"
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("tp,dp", [(2, 1), (2, 2)])
+def test_c1_shape_vs_oracle_world(tp, dp, precision, tmp_path):
+    """BASELINE configs[1] shape (L6 d384 H6 ctx256 vocab65) under tp2 (x dp2): 3 training steps, every rank
+    against the oracle's emulated world, computed here (a few seconds).  In bf16 mode this is the path
+    SCALE times: GEMM-epilogue peer push + device barrier + reduction inside LayerNorm."""
+    _need_gpus(tp * dp)
+    sys.path.insert(0, str(GOLDEN))
+    import make_config_golden as mk
+
+    vec = tmp_path / "config_c1.npz"
+    mk.main("c1", spec=dict(tp=tp, dp=dp, global_batch=2 * dp, steps=3), out_path=vec)
+    outs = _run_world(CONFIG_WORKER, ["c1", vec, precision], tp * dp, timeout=240)
+    if precision == "bf16":
+        assert "path peer-push" in outs[0] or os.environ.get("NUMPITRON_TP_PEER") == "0", outs[0][-500:]
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("config", ["c3", "c4"])
+def test_baseline_config_vs_oracle_world(config, precision):
+    """BASELINE configs[2] (GPT-2 small, tp=8: one local head of dim 96, V_local 6283/6282) and configs[3]
+    (GPT-2 medium, tp2 x dp4: the 102.9 MB data-parallel all-reduce of the tied embedding gradient) at a
+    reduced batch against the committed oracle vectors (tests/golden/config_c*.npz)."""
+    _need_gpus(8)
+    _run_world(CONFIG_WORKER, [config, GOLDEN / f"config_{config}.npz", precision], 8, timeout=600)

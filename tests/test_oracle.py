@@ -3,7 +3,7 @@ UNMODIFIED reference (tests/golden/make_golden.py).  literal=True must be bit-ex
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, load_golden
+from conftest import GOLDEN, ROOT, load_golden
 from oracle import numpitron_oracle as O
 
 TINY = dict(d_model=32, n_heads=4, n_layers=2, vocab=17, seq_len=16)
@@ -200,3 +200,74 @@ def test_oracle_sampling_from_reference_checkpoint(tp):
     assert O.generate(model, [3], 24, None, None) == G["greedy"].tolist()
     for name, temp in (("basic_t1", 1.0), ("basic_t40", 40.0)):
         assert O.generate(model, [3], 24, temp, np.random.default_rng(42)) == G[name].tolist(), name
+
+
+def test_package_synthetic_data_matches_oracle():
+    """numpitron_b200.data.synthetic (what bench.py and the multi-GPU tests draw their batches with) is the
+    oracle's token stream and batch draw, which test_draw_batch_matches_reference_loader pins to the reference."""
+    from numpitron_b200.data import synthetic as S
+
+    np.testing.assert_array_equal(S.synthetic_tokens(65, 10000), O.synthetic_tokens(65, 10000))
+    data = S.synthetic_tokens(17, 5000)
+    for seed in (0, 99):
+        a = S.draw_batch(data, np.random.default_rng(seed), 6, 16)
+        b = O.draw_batch(data, np.random.default_rng(seed), 6, 16)
+        np.testing.assert_array_equal(a[0], b[0])
+        np.testing.assert_array_equal(a[1], b[1])
+    x = np.arange(24).reshape(8, 3)
+    np.testing.assert_array_equal(S.local_rows(x, 4, 2), x[4:6])
+
+
+def test_workloads_and_config_vectors():
+    """The BASELINE workloads partition like the reference (arange(world).reshape(pp, dp, tp)) and the committed
+    oracle vectors for configs[2] / configs[3] have the layout the multi-GPU test and bench.py's parity leg read."""
+    from numpitron_b200.workloads import WORKLOADS, flop_per_token, partition
+
+    assert partition("c1", 1) == (1, 1) and partition("c1", 8) == (2, 4) and partition("c3", 8) == (8, 1)
+    assert partition("c4", 8) == (2, 4) and partition("c1", 4, tp=1) == (1, 4)
+    assert abs(flop_per_token(WORKLOADS["c1"]["model"]) - 70.93e6) < 0.01e6          # SURVEY §8(d)
+    assert abs(flop_per_token(WORKLOADS["c3"]["model"]) - 854.4e6) < 0.1e6
+    assert abs(flop_per_token(WORKLOADS["c3"]["model"], causal_skip=True) - 797.8e6) < 0.1e6
+    for cfg, (tp, dp) in (("c3", (8, 1)), ("c4", (2, 4))):
+        f = GOLDEN / f"config_{cfg}.npz"
+        if not f.exists():
+            pytest.skip(f"{f.name} not generated")
+        z = np.load(f)
+        m = WORKLOADS[cfg]["model"]
+        assert (int(z["tp"]), int(z["dp"])) == (tp, dp)
+        V_local = [len(c) for c in np.array_split(np.arange(m["vocab_size"]), tp)]
+        for i in range(int(z["steps"])):
+            assert z[f"x{i}"].shape == (int(z["global_batch"]), m["seq_len"]) and z[f"x{i}"].dtype == np.uint16
+            for d in range(dp):
+                loss = z[f"loss{i}/dp{d}"]
+                assert loss.shape == (int(z["global_batch"]) // dp, m["seq_len"]) and np.all(np.isfinite(loss))
+        for r in range(tp * dp):
+            assert z[f"rank{r}/logits0_rowsum"].size == int(z["global_batch"]) // dp * m["seq_len"]
+            assert z[f"rank{r}/dE0"].shape == z[f"rank{r}/E_final"].shape
+            assert z[f"rank{r}/dE0"].shape[1] == min(int(z["e_cols"]), V_local[r % tp])
+
+
+def test_reference_world_runs_the_unmodified_reference():
+    """bench.py's reference arm: baseline/_ref (pip-installed from /root/reference) under oracle/mpi4py_stub, two
+    OS processes tp2: its losses are the oracle's for the same world, batches and settings."""
+    import bench
+    from numpitron_b200.data.synthetic import draw_batch, synthetic_tokens
+
+    if not (ROOT / "baseline" / "_ref" / "numpitron").exists():
+        pytest.skip("baseline/_ref not installed (baseline/install_reference.sh)")
+    from numpitron_b200 import workloads
+
+    tiny = dict(name="tiny", model=dict(d_model=32, n_heads=4, n_layers=2, vocab_size=17, seq_len=16), seqs_per_gpu=2, sweep=None)
+    workloads.WORKLOADS["tiny"] = tiny
+    try:
+        r = bench.run_reference_world("tiny", 2, steps=3, warmup=0, budget_s=60.0, seqs_per_replica=2)
+    finally:
+        workloads.WORKLOADS.pop("tiny")
+    assert r["steps"] == 3 and r["tp"] == 2 and r["dp"] == 1 and r["value"] > 0
+    # the same three steps on the oracle's emulated tp2 world: the reference's DataLoader draws with the model's rng
+    rng = np.random.default_rng(42)
+    orc = O.OracleTransformer(32, 4, 2, 17, 16, rng=rng, tp=2, dp=1, literal=True, lr=workloads.LR, beta1=workloads.BETA1,
+                              beta2=workloads.BETA2)
+    data = synthetic_tokens(17)
+    want = [float(orc.train_step(*draw_batch(data, rng, 2, 16))[0]) for _ in range(3)]
+    np.testing.assert_allclose(r["losses"], want, rtol=1e-6)

@@ -256,3 +256,59 @@ def test_sampling_matches_reference():
     assert generate(t, [3], 24, None, None, 17) == G["greedy"].tolist()
     for name, temp in (("basic_t1", 1.0), ("basic_t40", 40.0)):
         assert generate(t, [3], 24, temp, np.random.default_rng(42), 17) == G[name].tolist(), name
+
+
+def test_graph_survives_checkpoint(tmp_path):
+    """A reference-style loop checkpoints between training steps (train_shakespeare.py:118-126):
+    save_checkpoint() gathers and re-scatters the model and the optimizer, which replaces every parameter /
+    moment buffer.  The captured graph must notice (nn.core.storage_generation) and re-capture on the new
+    storage instead of training the orphaned buffers: graphed == eager, before and after the checkpoint."""
+    from numpitron_b200.checkpoint import save_checkpoint
+
+    rng = np.random.default_rng(11)
+    xs = [rng.integers(0, 17, (4, 16)).astype(np.uint16) for _ in range(10)]
+    ys = [rng.integers(0, 17, (4, 16)).astype(np.uint16) for _ in range(10)]
+    t1, o1 = build(TINY)
+    t2, o2 = build(TINY)
+    g = GraphedTrainStep(t2, o2, 4, 16, warmup=2)
+    eager, graphed = [], []
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        if i == 5:
+            save_checkpoint(t1, o1, 0, 0.0, tmp_path / "a.npy")
+            save_checkpoint(t2, o2, 0, 0.0, tmp_path / "b.npy")
+            assert g.graph is not None   # it was captured before the checkpoint
+        eager.append(train_step(t1, o1, x, y))
+        graphed.append(g.step(x, y))
+    assert g.graph is not None   # ... and re-captured after it
+    np.testing.assert_array_equal(np.float32(eager), np.float32(graphed))
+    np.testing.assert_array_equal(to_numpy(t1.input_embedding.embedding.data), to_numpy(t2.input_embedding.embedding.data))
+    np.testing.assert_array_equal(to_numpy(t1.block_1.mlp.row_linear.weight.data), to_numpy(t2.block_1.mlp.row_linear.weight.data))
+    a = np.load(tmp_path / "a.npy", allow_pickle=True)[()]
+    b = np.load(tmp_path / "b.npy", allow_pickle=True)[()]
+    _tree_equal(a, b)
+
+
+def test_loader_feeds_graphed_step_without_host_sync(tmp_path):
+    """DataLoader.next_batch launches its gather on the caller's stream; load_resident copies on the step's
+    own stream.  No host synchronisation in between: the stream ordering alone must make the batches arrive."""
+    from numpitron_b200.data import DataLoader
+
+    data = np.random.default_rng(1234).integers(0, 17, 50000).astype(np.uint16)
+    path = tmp_path / "tokens.bin"
+    data.tofile(path)
+    t1, o1 = build(TINY)
+    t2, o2 = build(TINY)
+    dl1 = DataLoader(path, 16, 4, np.random.default_rng(5))
+    dl2 = DataLoader(path, 16, 4, np.random.default_rng(5))
+    g = GraphedTrainStep(t2, o2, 4, 16, warmup=2)
+    want, got = [], []
+    for _ in range(8):
+        x, y = dl1.next_batch()
+        want.append(train_step(t1, o1, x, y))
+    for _ in range(8):
+        g.load_resident(*dl2.next_batch())
+        g.step_resident_async()
+        got.append(g.loss_dev.clone())   # same stream order as the step? no: read after the final sync below
+    g.stream.synchronize()
+    np.testing.assert_array_equal(to_numpy(t1.input_embedding.embedding.data), to_numpy(t2.input_embedding.embedding.data))
+    assert float(g.loss_dev.item()) == want[-1]
