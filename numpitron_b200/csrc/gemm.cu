@@ -96,8 +96,14 @@ splitk_reduce_vec_kernel(const float* __restrict__ partial, GemmEpilogue e, int 
   epi_store4(e, b, m, n, acc);
 }
 
+// NPT_GEMM_TF32X3_TC runs on the tensor cores when TMA can address the operands, else on the FFMA kernel
+static bool use_simt(const npt_gemm_args& a) {
+  return a.mode == NPT_GEMM_FP32_SIMT || (a.mode == NPT_GEMM_TF32X3_TC && !gemm_tf32_supported(a));
+}
+
 static int choose_splits(const npt_gemm_args& a) {
-  if (a.mode == NPT_GEMM_FP32_SIMT) return gemm_simt_splits(a);
+  if (use_simt(a)) return gemm_simt_splits(a);
+  if (a.mode == NPT_GEMM_TF32X3_TC) return gemm_tf32_splits(a);
   return gemm_tc_splits(a);
 }
 
@@ -137,8 +143,11 @@ int npt_gemm(const npt_gemm_args* args, void* stream) {
     NPT_REQUIRE(!a.relu_bits_out || a.relu, "gemm: relu_bits_out needs relu = 1");
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (a.mode != NPT_GEMM_FP32_SIMT) {
+  NPT_REQUIRE(a.mode >= NPT_GEMM_FP32_SIMT && a.mode <= NPT_GEMM_TF32X3_TC, "gemm: unknown mode %d", a.mode);
+  if (a.mode == NPT_GEMM_BF16_TC) {
     if (int rc = gemm_tc_supported(a)) return rc;
+  } else {
+    NPT_REQUIRE(!a.C_bf16_peer && !a.relu_bits_out && !a.mask_bits, "gemm: peer stores / packed ReLU bits need the bf16 tensor-core mode");
   }
   const GemmEpilogue epi = make_epilogue(a);
   const int splits = choose_splits(a);
@@ -152,7 +161,8 @@ int npt_gemm(const npt_gemm_args* args, void* stream) {
     NPT_REQUIRE(aligned16(a.workspace), "gemm: workspace must be 16-byte aligned");
     partial = (float*)a.workspace;
   }
-  int rc = (a.mode == NPT_GEMM_FP32_SIMT) ? gemm_simt_launch(a, epi, splits, partial, st)
+  int rc = use_simt(a) ? gemm_simt_launch(a, epi, splits, partial, st)
+           : a.mode == NPT_GEMM_TF32X3_TC ? gemm_tf32_launch(a, epi, splits, partial, st)
                                           : gemm_tc_launch(a, epi, splits, partial, st);
   if (rc) return rc;
   if (splits > 1 && !a.skip_splitk_reduce) {

@@ -104,5 +104,9 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
 int gemm_tc_supported(const npt_gemm_args& a);  // 0 = ok, else sets error
 int gemm_simt_splits(const npt_gemm_args& a);
 int gemm_tc_splits(const npt_gemm_args& a);
+// 3xTF32 tensor-core kernel (gemm_tf32.cu)
+bool gemm_tf32_supported(const npt_gemm_args& a);
+int gemm_tf32_splits(const npt_gemm_args& a);
+int gemm_tf32_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, float* partial, cudaStream_t st);
 
 }  // namespace npt

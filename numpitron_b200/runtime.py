@@ -13,9 +13,9 @@ import torch
 
 from . import _lib
 
-FP32 = "fp32"   # fp32-accurate mode (NPT_GEMM_FP32_SIMT)
+FP32 = "fp32"   # fp32-accurate mode: 3xTF32 on tcgen05 (NPT_GEMM_TF32X3_TC); NUMPITRON_FP32_GEMM=simt -> fp32 FFMA
 BF16 = "bf16"   # bf16 operands on tcgen05, fp32 accumulate / residual stream / norms / loss / Adam
-_GEMM_MODE = {FP32: 0, BF16: 1}
+_GEMM_MODE = {FP32: 0 if os.environ.get("NUMPITRON_FP32_GEMM", "tf32x3") == "simt" else 2, BF16: 1}
 
 _state = {"precision": os.environ.get("NUMPITRON_PRECISION", FP32), "workspace": None, "device": None}
 

@@ -40,7 +40,8 @@ def bf16_round(a):
 # ---------------------------------------------------------------------------------------------
 def run_gemm(mode, M, N, K, ta, tb, seed=0, alpha=1.0, bias=False, relu=False, mask=False, bf16_out=False):
     rng = np.random.default_rng(seed)
-    pad = (lambda n: (n + 7) // 8 * 8) if mode == 1 else (lambda n: n)
+    # leading dimensions TMA can address: multiples of 8 bf16 / 4 fp32 (mode 2 on odd pitches runs the FFMA kernel)
+    pad = (lambda n: (n + 7) // 8 * 8) if mode == 1 else ((lambda n: (n + 3) // 4 * 4) if mode == 2 else (lambda n: n))
     a_shape = (K, M) if ta else (M, K)
     b_shape = (N, K) if tb else (K, N)
     lda, ldb = pad(a_shape[1]), pad(b_shape[1])
@@ -89,6 +90,34 @@ def test_gemm_fp32_splitk_and_epilogue():
     assert run_gemm(0, 256, 384, 96, False, False, alpha=0.5, bias=True, relu=True) < 2e-6
     assert run_gemm(0, 256, 384, 96, False, True, mask=True) < 2e-6
     assert run_gemm(0, 130, 70, 4096, True, False, bias=True) < 5e-6  # split-K + ragged + bias
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("shape", [(128, 128, 32), (128, 64, 128), (256, 384, 384), (200, 72, 136), (1, 1, 1), (300, 257, 1000),
+                                   (4096, 1152, 384), (130, 40, 20)])
+def test_gemm_tf32x3_tcgen05(shape, ta, tb):
+    """fp32-accurate tensor-core mode: fp32 operands split hi/lo inside the kernel, three kind::tf32 MMAs per
+    k-step, fp32 TMEM accumulator — fp32-level error (north star: per-layer rel 1e-4; FFMA lands at ~1e-6)."""
+    assert run_gemm(2, *shape, ta, tb) < 5e-6
+
+
+def test_gemm_tf32x3_splitk_and_epilogue():
+    # long K: the tensor core adds into the TMEM accumulator with truncation, so the error grows with the chain
+    # length; split-K caps a chain at 1024 k and the partials are added in fp32 round-to-nearest
+    assert run_gemm(2, 384, 1152, 8192, True, False) < 1e-5          # dW shape -> split-K path
+    assert run_gemm(2, 256, 384, 96, False, False, alpha=0.5, bias=True, relu=True) < 5e-6
+    assert run_gemm(2, 256, 384, 96, False, True, mask=True) < 5e-6
+    assert run_gemm(2, 130, 72, 4096, True, False, bias=True) < 5e-6  # split-K + ragged + bias
+    # hard case for a split scheme: large common offset, tiny signal (the reference's activations: mean >> std)
+    rng = np.random.default_rng(3)
+    A = (1.0 + 1e-3 * rng.standard_normal((512, 384))).astype(np.float32)
+    B = (0.003 + 1e-4 * rng.standard_normal((384, 256))).astype(np.float32)
+    C = rt.empty((512, 256))
+    ops.gemm(dev(A), dev(B), 512, 256, 384, lda=384, ldb=256, C_out=C, ldc=256, mode=2)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    want32 = A @ B
+    err, err32 = np.abs(host(C) - ref).max() / np.abs(ref).max(), np.abs(want32 - ref).max() / np.abs(ref).max()
+    assert err < max(4 * err32, 1e-6), (err, err32)
 
 
 @pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
@@ -202,7 +231,7 @@ def test_gemm_packed_relu_bits(M, K, N):
     np.testing.assert_array_equal(host(ab), host(bb))
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_gemm_batched_head_layout(mode):
     """q@k^T and p@v addressed in place inside the (B,S,h,3,Dh) projection output (attention.py:43-52)."""
     rng = np.random.default_rng(5)
