@@ -1,5 +1,5 @@
 // Fused causal attention for sm_100a (bf16 mode): forward and backward without ever writing the
-// (B,h,S,S) score / probability matrices to HBM.  Replaces, for head_dim 64 and S % 128 == 0,
+// (B,h,S,S) score / probability matrices to HBM.  Replaces, for head_dim 64 or 96 and S % 128 == 0,
 //   forward : q@k^T / sqrt(d_model) -> causal mask -> softmax -> p@v        nn/attention.py:43-52
 //   backward: dV = p^T@dO, dP = dO@v^T, softmax backward, mask, scale,
 //             dQ = dS@k, dK = dS^T@q, concat([dq,dk,dv])                      nn/attention.py:81-98
@@ -20,14 +20,50 @@
 //   dkv : item = (b, head, 128 keys); steps = query tiles diag..last; dK, dV accumulate in TMEM.
 //   dq  : item = (b, head, 128 queries); steps = key tiles 0..diag; dQ accumulates in TMEM.
 // No atomics: every output element has exactly one writer and a fixed summation order.
+//
+// head_dim is a template parameter.  A {128 rows x Dh} operand tile is NCH column chunks of CH columns, each
+// chunk one TMA box with rows of CH * 2 bytes = one swizzle row: Dh = 64 -> one 128-byte-swizzled chunk;
+// Dh = 96 (GPT-2 small under tp = 8: ONE local head of 96, nn/attention.py:37-45) -> three
+// 64-byte-swizzled chunks of 32 columns.  The same bytes are read K-major (contraction over Dh: chunk by
+// chunk, 16 columns per MMA) or MN-major (Dh is the N extent: one MMA spans the chunks, LBO = chunk pitch).
 #include "tc_ptx.cuh"
 
 namespace npt {
 using namespace tc;
 
 constexpr int AT_THREADS = 192;
-constexpr int AT_TILE = 128 * 64 * 2;  // one {64 x 128} bf16 TMA box = 16 KB
-constexpr int AT_DH = 64;
+constexpr int AT_PTILE = 128 * 128 * 2;  // a 128 x 128 bf16 P / dS tile: two 64-column halves, 128-byte swizzle
+
+template <int DH>
+struct AttnCfg {
+  static_assert(DH == 64 || DH == 96, "fused attention: head_dim 64 or 96");
+  static constexpr int CH = (DH % 64 == 0) ? 64 : 32;      // columns per chunk (= TMA box width)
+  static constexpr int NCH = DH / CH;
+  static constexpr int RB = CH * 2;                          // bytes per swizzle row
+  static constexpr int CHUNK = 128 * RB;                     // bytes per chunk
+  static constexpr int TILE = NCH * CHUNK;                   // 128 x DH bf16
+  static constexpr uint32_t LAYOUT = (CH == 64) ? 2u : 4u;   // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
+  static constexpr uint32_t SBO = 8 * RB;                    // 8-row group pitch
+};
+// K-major read of a {128 x DH} tile, 16-column step kk of the contraction over DH
+template <int DH>
+__device__ __forceinline__ uint64_t desc_k(uint32_t tile, int kk) {
+  using C = AttnCfg<DH>;
+  const int e = kk * 16;
+  return make_smem_desc_l(tile + (e / C::CH) * C::CHUNK, 16, C::SBO, C::LAYOUT) + (uint64_t)(((e % C::CH) * 2) >> 4);
+}
+// MN-major read (DH = the N extent, rows = the contraction index), 16-row step kk
+template <int DH>
+__device__ __forceinline__ uint64_t desc_mn(uint32_t tile, int kk) {
+  using C = AttnCfg<DH>;
+  return make_smem_desc_l(tile, C::CHUNK, C::SBO, C::LAYOUT) + (uint64_t)(kk * ((16 * C::RB) >> 4));
+}
+template <int DH>
+__device__ __forceinline__ void load_tile(const CUtensorMap* map, uint64_t* bar, uint8_t* dst, int col, int row) {
+  using C = AttnCfg<DH>;
+#pragma unroll
+  for (int c = 0; c < C::NCH; ++c) tma_load_4d(map, bar, dst + c * C::CHUNK, col + c * C::CH, row, 0, 0);
+}
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) { return pack_bf16(a, b); }
 __device__ __forceinline__ float ex2f(float x) {
@@ -88,16 +124,19 @@ struct Cursor {
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+template <int DH>
 struct AttnFwdSmem {
-  static constexpr int Q = 0, K = 2 * AT_TILE, V = 4 * AT_TILE, P = 6 * AT_TILE, BAR = 10 * AT_TILE;
+  static constexpr int T = AttnCfg<DH>::TILE;
+  static constexpr int Q = 0, K = 2 * T, V = 4 * T, P = 6 * T, BAR = 6 * T + 2 * AT_PTILE;
   static constexpr int TOTAL = BAR + 24 * 8 + 16 + 1024;
 };
 
+template <int DH>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out,
                 float* __restrict__ lse, int B, int S, int h, float inv_div) {
-  constexpr int DH = AT_DH;
-  using L = AttnFwdSmem;
+  using L = AttnFwdSmem<DH>;
+  constexpr int AT_TILE = L::T;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
@@ -126,7 +165,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
   const uint32_t tmem = *tmem_slot;
   pdl_wait();     // set-up above is private; global memory is touched only from here on
   pdl_trigger();  // persistent grid: the next kernel may be scheduled behind this one
-  // TMEM columns: S[2] at 0 / 128, O[2] at 256 / 320
+  // TMEM columns: S[2] at 0 / 128, O[2] at 256 / 256 + DH
 
   if (warp == 0) {
     if (lane == 0) {
@@ -138,14 +177,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
           const int qb = c.wi & 1;
           mbar_wait(q_empty + qb, ((c.wi >> 1) & 1) ^ 1);
           mbar_expect_tx(q_full + qb, AT_TILE);
-          tma_load_4d(&tmQKV, q_full + qb, smem + L::Q + qb * AT_TILE, col_q, row0 + c.tile * 128, 0, 0);
+          load_tile<DH>(&tmQKV, q_full + qb, smem + L::Q + qb * AT_TILE, col_q, row0 + c.tile * 128);
         }
         const int st = c.t & 1;
         mbar_wait(kv_empty + st, ((c.t >> 1) & 1) ^ 1);
         mbar_expect_tx(k_full + st, AT_TILE);
-        tma_load_4d(&tmQKV, k_full + st, smem + L::K + st * AT_TILE, col_q + DH, row0 + c.j * 128, 0, 0);
+        load_tile<DH>(&tmQKV, k_full + st, smem + L::K + st * AT_TILE, col_q + DH, row0 + c.j * 128);
         mbar_expect_tx(v_full + st, AT_TILE);
-        tma_load_4d(&tmQKV, v_full + st, smem + L::V + st * AT_TILE, col_q + 2 * DH, row0 + c.j * 128, 0, 0);
+        load_tile<DH>(&tmQKV, v_full + st, smem + L::V + st * AT_TILE, col_q + 2 * DH, row0 + c.j * 128);
       }
     }
   } else if (warp == 1) {
@@ -158,10 +197,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
         mbar_wait(k_full + st, ph);
         mbar_wait(s_empty + st, ph ^ 1);  // softmax threads have drained this S buffer (two steps ago)
         fence_after();
-        const uint64_t dq = make_smem_desc(smem_u32(smem + L::Q + qb * AT_TILE), 16, 1024);
-        const uint64_t dk = make_smem_desc(smem_u32(smem + L::K + st * AT_TILE), 16, 1024);
+        const uint32_t tq = smem_u32(smem + L::Q + qb * AT_TILE), tk = smem_u32(smem + L::K + st * AT_TILE);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem + st * 128, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0);
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem + st * 128, desc_k<DH>(tq, k), desc_k<DH>(tk, k), idesc_s, k > 0);
         umma_commit(s_full + st);
         if (c.last_step()) umma_commit(q_empty + qb);
       };
@@ -175,12 +213,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
         mbar_wait(v_full + st, ph);
         mbar_wait(p_full + st, ph);
         fence_after();
-        const uint32_t sp = smem_u32(smem + L::P + st * 2 * AT_TILE);
-        const uint64_t dv = make_smem_desc(smem_u32(smem + L::V + st * AT_TILE), 16384, 1024);
+        const uint32_t sp = smem_u32(smem + L::P + st * AT_PTILE);
+        const uint32_t tv = smem_u32(smem + L::V + st * AT_TILE);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // 128 keys = 8 x 16
           const uint64_t dp = make_smem_desc(sp + (k >> 2) * 16384, 16, 1024) + (uint64_t)((k & 3) * 2);
-          umma_bf16(tmem + 256 + st * 64, dp, dv + (uint64_t)(k * 128), idesc_o, k > 0);
+          umma_bf16(tmem + 256 + st * DH, dp, desc_mn<DH>(tv, k), idesc_o, k > 0);
         }
         umma_commit(pv_done + st);
         umma_commit(kv_empty + st);
@@ -202,8 +240,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
 #pragma unroll
         for (int d = 0; d < DH; ++d) o[d] = 0.f;
       }
-      const uint32_t tS = tmem + st * 128 + lane_addr, tO = tmem + 256 + st * 64 + lane_addr;
-      const uint32_t sP = smem_u32(smem + L::P + st * 2 * AT_TILE);
+      const uint32_t tS = tmem + st * 128 + lane_addr, tO = tmem + 256 + st * DH + lane_addr;
+      const uint32_t sP = smem_u32(smem + L::P + st * AT_PTILE);
       mbar_wait(s_full + st, ph);
       fence_after();
       // The whole 128-wide score row goes to registers in one shot, so the TMEM buffer is handed back
@@ -215,46 +253,86 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       // loaded nor exponentiated, only zero-filled in P.  (At S = 256 two of every three key tiles are
       // diagonal ones; masking every element cost 8.5 instructions per score against 3.5.)
       const int n_live = diag ? quarter + 1 : 4;  // chunks with any visible column (warp-uniform)
-      uint32_t r[4][32];
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
-        if (cc < n_live) tmem_ld_32x32(tS + cc * 32, r[cc]);
-      tmem_ld_wait();
-      fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty + st);
-      if (diag) {  // the triangle: masked scores become -inf once (2^-inf = 0), the math below is mask-free
+      float m_new, alpha, sum = 0.f;
+      if constexpr (DH <= 64) {
+        uint32_t r[4][32];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc)
-          if (cc == quarter) {
+          if (cc < n_live) tmem_ld_32x32(tS + cc * 32, r[cc]);
+        tmem_ld_wait();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty + st);
+        if (diag) {  // the triangle: masked scores become -inf once (2^-inf = 0), the math below is mask-free
 #pragma unroll
-            for (int t = 0; t < 32; ++t) r[cc][t] = (t <= lane) ? r[cc][t] : 0xff800000u;
-          }
-      }
-      float mx = -INFINITY;
+          for (int cc = 0; cc < 4; ++cc)
+            if (cc == quarter) {
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
-        if (cc < n_live) {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(r[cc][t]));
+              for (int t = 0; t < 32; ++t) r[cc][t] = (t <= lane) ? r[cc][t] : 0xff800000u;
+            }
         }
-      const float m_new = fmaxf(m_run, mx * k2);  // k2 > 0, so max commutes with the scaling
-      const float alpha = c.first_step() ? 0.f : ex2f(m_run - m_new);
-      float sum = 0.f;
+        float mx = -INFINITY;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        float p[32];
-        if (cc < n_live) {
+        for (int cc = 0; cc < 4; ++cc)
+          if (cc < n_live) {
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            p[t] = ex2f(fmaf(__uint_as_float(r[cc][t]), k2, -m_new));
-            sum += p[t];
+            for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(r[cc][t]));
           }
-        } else {
+        m_new = fmaxf(m_run, mx * k2);  // k2 > 0, so max commutes with the scaling
+        alpha = c.first_step() ? 0.f : ex2f(m_run - m_new);
 #pragma unroll
-          for (int t = 0; t < 32; ++t) p[t] = 0.f;
+        for (int cc = 0; cc < 4; ++cc) {
+          float p[32];
+          if (cc < n_live) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              p[t] = ex2f(fmaf(__uint_as_float(r[cc][t]), k2, -m_new));
+              sum += p[t];
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) p[t] = 0.f;
+          }
+          store_row_chunk(sP, row, cc, p);
         }
-        store_row_chunk(sP, row, cc, p);
+      } else {
+        // Dh = 96: the 96 output accumulators leave no room for the whole score row in registers; two passes
+        // over the TMEM buffer (row max, then the exponentials), 32 columns at a time; the buffer goes back
+        // to the MMA warp after the second pass.
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int cc = 0; cc < n_live; ++cc) {
+          uint32_t r[32];
+          tmem_ld_32x32(tS + cc * 32, r);
+          tmem_ld_wait();
+          const bool tri = diag && cc == quarter;
+#pragma unroll
+          for (int t = 0; t < 32; ++t) mx = fmaxf(mx, (tri && t > lane) ? -INFINITY : __uint_as_float(r[t]));
+        }
+        m_new = fmaxf(m_run, mx * k2);
+        alpha = c.first_step() ? 0.f : ex2f(m_run - m_new);
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          float p[32];
+          if (cc < n_live) {
+            uint32_t r[32];
+            tmem_ld_32x32(tS + cc * 32, r);
+            tmem_ld_wait();
+            const bool tri = diag && cc == quarter;
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              p[t] = (tri && t > lane) ? 0.f : ex2f(fmaf(__uint_as_float(r[t]), k2, -m_new));
+              sum += p[t];
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) p[t] = 0.f;
+          }
+          store_row_chunk(sP, row, cc, p);
+        }
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty + st);
       }
       l_run = l_run * alpha + sum;
       m_run = m_new;
@@ -299,8 +377,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: D[b,h,s] = sum_d dO*O   (8 lanes per row of 64)
+// backward: D[b,h,s] = sum_d dO*O   (8 lanes per row of Dh)
 // ------------------------------------------------------------------------------------------------
+template <int DH>
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                      float* __restrict__ D, int64_t rows /* B*S*h */, int S, int h) {
@@ -308,16 +387,20 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* _
   pdl_trigger();
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const int part = threadIdx.x & 7;
+  constexpr int PER = DH / 8;   // elements per lane: 8 or 12 (8-byte aligned)
   float acc = 0.f;
   if (r < rows) {
-    const uint4 a = *reinterpret_cast<const uint4*>(o + r * 64 + part * 8);
-    const uint4 g = *reinterpret_cast<const uint4*>(d_o + r * 64 + part * 8);
-    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-    const __nv_bfloat162* pg = reinterpret_cast<const __nv_bfloat162*>(&g);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 x = __bfloat1622float2(pa[i]), y = __bfloat1622float2(pg[i]);
-      acc += x.x * y.x + x.y * y.y;
+    for (int i = 0; i < PER / 4; ++i) {
+      const uint2 a = *reinterpret_cast<const uint2*>(o + r * DH + part * PER + i * 4);
+      const uint2 g = *reinterpret_cast<const uint2*>(d_o + r * DH + part * PER + i * 4);
+      const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+      const __nv_bfloat162* pg = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float2 x = __bfloat1622float2(pa[j]), y = __bfloat1622float2(pg[j]);
+        acc += x.x * y.x + x.y * y.y;
+      }
     }
   }
   acc += __shfl_xor_sync(kFull, acc, 1);
@@ -371,9 +454,10 @@ __device__ __forceinline__ void bwd_rows(uint32_t tS, uint32_t tdP, int row, boo
   }
 }
 
+template <int DH>
 __device__ __forceinline__ void store_acc_row(uint32_t taddr, __nv_bfloat16* dst) {
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
+  for (int c = 0; c < DH / 32; ++c) {
     uint32_t r[32];
     tmem_ld_32x32(taddr + c * 32, r);
     tmem_ld_wait();
@@ -392,18 +476,22 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, __nv_bfloat16* dst
 // ------------------------------------------------------------------------------------------------
 // backward dK / dV : item = (b, head, key tile j); steps = query tiles i = j .. nqt-1
 // ------------------------------------------------------------------------------------------------
+template <int DH>
 struct AttnDkvSmem {
-  static constexpr int K = 0, V = 2 * AT_TILE, Q = 4 * AT_TILE, DO = 6 * AT_TILE, P = 8 * AT_TILE, DS = 10 * AT_TILE,
-                       BAR = 12 * AT_TILE;
+  static constexpr int T = AttnCfg<DH>::TILE;
+  static constexpr int KVB = (DH <= 64) ? 2 : 1;   // K / V buffers (per item): double-buffered while they fit
+  static constexpr int K = 0, V = KVB * T, Q = 2 * KVB * T, DO = Q + 2 * T, P = DO + 2 * T, DS = P + AT_PTILE,
+                       BAR = DS + AT_PTILE;
   static constexpr int TOTAL = BAR + 24 * 8 + 16 + 1024;
 };
 
+template <int DH>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const float* __restrict__ lse, const float* __restrict__ D, __nv_bfloat16* __restrict__ dqkv,
                     int B, int S, int h, float inv_div) {
-  constexpr int DH = AT_DH;
-  using L = AttnDkvSmem;
+  using L = AttnDkvSmem<DH>;
+  constexpr int AT_TILE = L::T, KVB = L::KVB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
@@ -436,7 +524,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   const uint32_t tmem = *tmem_slot;
   pdl_wait();     // set-up above is private; global memory is touched only from here on
   pdl_trigger();  // persistent grid: the next kernel may be scheduled behind this one
-  const uint32_t tmem_S = tmem, tmem_dP = tmem + 128, tmem_dK = tmem + 256, tmem_dV = tmem + 320;
+  const uint32_t tmem_S = tmem, tmem_dP = tmem + 128, tmem_dK = tmem + 256, tmem_dV = tmem + 256 + DH;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -445,17 +533,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const int b = c.bh / h, hh = c.bh - b * h;
         const int col_q = hh * 3 * DH, row0 = b * S;
         if (c.first_step()) {
-          const int kb = c.wi & 1;
-          mbar_wait(kv_empty + kb, ((c.wi >> 1) & 1) ^ 1);
+          const int kb = c.wi % KVB;
+          mbar_wait(kv_empty + kb, ((c.wi / KVB) & 1) ^ 1);
           mbar_expect_tx(kv_full + kb, 2 * AT_TILE);
-          tma_load_4d(&tmQKV, kv_full + kb, smem + L::K + kb * AT_TILE, col_q + DH, row0 + c.tile * 128, 0, 0);
-          tma_load_4d(&tmQKV, kv_full + kb, smem + L::V + kb * AT_TILE, col_q + 2 * DH, row0 + c.tile * 128, 0, 0);
+          load_tile<DH>(&tmQKV, kv_full + kb, smem + L::K + kb * AT_TILE, col_q + DH, row0 + c.tile * 128);
+          load_tile<DH>(&tmQKV, kv_full + kb, smem + L::V + kb * AT_TILE, col_q + 2 * DH, row0 + c.tile * 128);
         }
         const int st = c.t & 1, i = c.tile + c.j;
         mbar_wait(qdo_empty + st, ((c.t >> 1) & 1) ^ 1);
         mbar_expect_tx(qdo_full + st, 2 * AT_TILE);
-        tma_load_4d(&tmQKV, qdo_full + st, smem + L::Q + st * AT_TILE, col_q, row0 + i * 128, 0, 0);
-        tma_load_4d(&tmDO, qdo_full + st, smem + L::DO + st * AT_TILE, hh * DH, row0 + i * 128, 0, 0);
+        load_tile<DH>(&tmQKV, qdo_full + st, smem + L::Q + st * AT_TILE, col_q, row0 + i * 128);
+        load_tile<DH>(&tmDO, qdo_full + st, smem + L::DO + st * AT_TILE, hh * DH, row0 + i * 128);
       }
     }
   } else if (warp == 1) {
@@ -464,19 +552,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       constexpr uint32_t idesc_a = make_idesc(DH, true, true);     // dV = P^T dO, dK = dS^T Q : both MN-major
       const uint32_t sp = smem_u32(smem + L::P), sds = smem_u32(smem + L::DS);
       auto issue_sdp = [&](const Cursor& c) {
-        const int st = c.t & 1, kb = c.wi & 1;
-        if (c.first_step()) mbar_wait(kv_full + kb, (c.wi >> 1) & 1);
+        const int st = c.t & 1, kb = c.wi % KVB;
+        if (c.first_step()) mbar_wait(kv_full + kb, (c.wi / KVB) & 1);
         mbar_wait(qdo_full + st, (c.t >> 1) & 1);
         mbar_wait(s_empty, (c.t & 1) ^ 1);  // threads have read S / dP of the previous step
         fence_after();
-        const uint64_t dq = make_smem_desc(smem_u32(smem + L::Q + st * AT_TILE), 16, 1024);
-        const uint64_t dk = make_smem_desc(smem_u32(smem + L::K + kb * AT_TILE), 16, 1024);
-        const uint64_t ddo = make_smem_desc(smem_u32(smem + L::DO + st * AT_TILE), 16, 1024);
-        const uint64_t dv = make_smem_desc(smem_u32(smem + L::V + kb * AT_TILE), 16, 1024);
+        const uint32_t tq = smem_u32(smem + L::Q + st * AT_TILE), tk = smem_u32(smem + L::K + kb * AT_TILE);
+        const uint32_t tdo = smem_u32(smem + L::DO + st * AT_TILE), tv = smem_u32(smem + L::V + kb * AT_TILE);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0);
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, desc_k<DH>(tq, k), desc_k<DH>(tk, k), idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_dP, ddo + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), idesc_s, k > 0);
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_dP, desc_k<DH>(tdo, k), desc_k<DH>(tv, k), idesc_s, k > 0);
         umma_commit(s_full);
       };
       Cursor cs, ca;
@@ -484,24 +570,27 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       ca = cs;
       if (cs.valid()) { issue_sdp(cs); cs.next(); }
       for (; ca.valid(); ca.next()) {
-        const int st = ca.t & 1, kb = ca.wi & 1;
+        const int st = ca.t & 1, kb = ca.wi % KVB;
         mbar_wait(pds_full, ca.t & 1);               // P / dS of this step are in shared memory (S / dP drained)
-        if (cs.valid()) { issue_sdp(cs); cs.next(); }  // next score tiles first: the threads are waiting for them
+        // next score tiles first: the threads are waiting for them.  With a single K / V buffer (Dh = 96) the first
+        // step of the NEXT item needs that buffer, which is released by the MMAs below: issue it after them.
+        const bool early = cs.valid() && (KVB > 1 || !cs.first_step());
+        if (early) { issue_sdp(cs); cs.next(); }
         if (ca.first_step()) mbar_wait(out_done, (ca.wi & 1) ^ 1);  // previous item's dK / dV were read out
         fence_after();
         // A = P^T / dS^T : MN-major (M = keys: two 64-key halves 16 KB apart; K = queries: 16 rows = 2048 B)
         // B = dO / Q tile : MN-major (N = Dh, K = queries: 16 rows = 2048 B)
         const uint64_t dpt = make_smem_desc(sp, 16384, 1024), ddst = make_smem_desc(sds, 16384, 1024);
-        const uint64_t dob = make_smem_desc(smem_u32(smem + L::DO + st * AT_TILE), 16384, 1024);
-        const uint64_t dqb = make_smem_desc(smem_u32(smem + L::Q + st * AT_TILE), 16384, 1024);
+        const uint32_t tdo = smem_u32(smem + L::DO + st * AT_TILE), tq = smem_u32(smem + L::Q + st * AT_TILE);
         const bool acc0 = !ca.first_step();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dV, dpt + (uint64_t)(k * 128), dob + (uint64_t)(k * 128), idesc_a, (acc0 || k > 0));
+        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dV, dpt + (uint64_t)(k * 128), desc_mn<DH>(tdo, k), idesc_a, (acc0 || k > 0));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dK, ddst + (uint64_t)(k * 128), dqb + (uint64_t)(k * 128), idesc_a, (acc0 || k > 0));
+        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dK, ddst + (uint64_t)(k * 128), desc_mn<DH>(tq, k), idesc_a, (acc0 || k > 0));
         umma_commit(acc_done);
         umma_commit(qdo_empty + st);
         if (ca.last_step()) umma_commit(kv_empty + kb);
+        if (!early && cs.valid()) { issue_sdp(cs); cs.next(); }
       }
     }
   } else {
@@ -530,8 +619,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         // rows of dK / dV are KEYS of tile j
         const int64_t k_glob = (int64_t)b * S + c.tile * 128 + row;
         __nv_bfloat16* base = dqkv + (k_glob * h + hh) * 3 * DH;
-        store_acc_row(tmem_dK + lane_addr, base + DH);
-        store_acc_row(tmem_dV + lane_addr, base + 2 * DH);
+        store_acc_row<DH>(tmem_dK + lane_addr, base + DH);
+        store_acc_row<DH>(tmem_dV + lane_addr, base + 2 * DH);
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(out_done);
@@ -549,17 +638,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // backward dQ : item = (b, head, query tile i); steps = key tiles j = 0 .. i
 // ------------------------------------------------------------------------------------------------
+template <int DH>
 struct AttnDqSmem {
-  static constexpr int Q = 0, DO = 2 * AT_TILE, K = 4 * AT_TILE, V = 6 * AT_TILE, DS = 8 * AT_TILE, BAR = 10 * AT_TILE;
+  static constexpr int T = AttnCfg<DH>::TILE;
+  static constexpr int Q = 0, DO = 2 * T, K = 4 * T, V = 6 * T, DS = 8 * T, BAR = 8 * T + AT_PTILE;
   static constexpr int TOTAL = BAR + 24 * 8 + 16 + 1024;
 };
 
+template <int DH>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const float* __restrict__ lse, const float* __restrict__ D, __nv_bfloat16* __restrict__ dqkv,
                    int B, int S, int h, float inv_div) {
-  constexpr int DH = AT_DH;
-  using L = AttnDqSmem;
+  using L = AttnDqSmem<DH>;
+  constexpr int AT_TILE = L::T;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
@@ -604,14 +696,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           const int qb = c.wi & 1;
           mbar_wait(qdo_empty + qb, ((c.wi >> 1) & 1) ^ 1);
           mbar_expect_tx(qdo_full + qb, 2 * AT_TILE);
-          tma_load_4d(&tmQKV, qdo_full + qb, smem + L::Q + qb * AT_TILE, col_q, row0 + c.tile * 128, 0, 0);
-          tma_load_4d(&tmDO, qdo_full + qb, smem + L::DO + qb * AT_TILE, hh * DH, row0 + c.tile * 128, 0, 0);
+          load_tile<DH>(&tmQKV, qdo_full + qb, smem + L::Q + qb * AT_TILE, col_q, row0 + c.tile * 128);
+          load_tile<DH>(&tmDO, qdo_full + qb, smem + L::DO + qb * AT_TILE, hh * DH, row0 + c.tile * 128);
         }
         const int st = c.t & 1;
         mbar_wait(kv_empty + st, ((c.t >> 1) & 1) ^ 1);
         mbar_expect_tx(kv_full + st, 2 * AT_TILE);
-        tma_load_4d(&tmQKV, kv_full + st, smem + L::K + st * AT_TILE, col_q + DH, row0 + c.j * 128, 0, 0);
-        tma_load_4d(&tmQKV, kv_full + st, smem + L::V + st * AT_TILE, col_q + 2 * DH, row0 + c.j * 128, 0, 0);
+        load_tile<DH>(&tmQKV, kv_full + st, smem + L::K + st * AT_TILE, col_q + DH, row0 + c.j * 128);
+        load_tile<DH>(&tmQKV, kv_full + st, smem + L::V + st * AT_TILE, col_q + 2 * DH, row0 + c.j * 128);
       }
     }
   } else if (warp == 1) {
@@ -625,14 +717,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         mbar_wait(kv_full + st, (c.t >> 1) & 1);
         mbar_wait(s_empty, (c.t & 1) ^ 1);
         fence_after();
-        const uint64_t dq = make_smem_desc(smem_u32(smem + L::Q + qb * AT_TILE), 16, 1024);
-        const uint64_t dk = make_smem_desc(smem_u32(smem + L::K + st * AT_TILE), 16, 1024);
-        const uint64_t ddo = make_smem_desc(smem_u32(smem + L::DO + qb * AT_TILE), 16, 1024);
-        const uint64_t dv = make_smem_desc(smem_u32(smem + L::V + st * AT_TILE), 16, 1024);
+        const uint32_t tq = smem_u32(smem + L::Q + qb * AT_TILE), tk = smem_u32(smem + L::K + st * AT_TILE);
+        const uint32_t tdo = smem_u32(smem + L::DO + qb * AT_TILE), tv = smem_u32(smem + L::V + st * AT_TILE);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0);
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, desc_k<DH>(tq, k), desc_k<DH>(tk, k), idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_dP, ddo + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), idesc_s, k > 0);
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_dP, desc_k<DH>(tdo, k), desc_k<DH>(tv, k), idesc_s, k > 0);
         umma_commit(s_full);
       };
       Cursor cs, ca;
@@ -645,12 +735,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         if (cs.valid()) { issue_sdp(cs); cs.next(); }
         if (ca.first_step()) mbar_wait(out_done, (ca.wi & 1) ^ 1);
         fence_after();
-        const uint64_t dkb = make_smem_desc(smem_u32(smem + L::K + st * AT_TILE), 16384, 1024);
+        const uint32_t tk = smem_u32(smem + L::K + st * AT_TILE);
         const bool acc0 = !ca.first_step();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t dds = make_smem_desc(sds + (k >> 2) * 16384, 16, 1024) + (uint64_t)((k & 3) * 2);
-          umma_bf16(tmem_dQ, dds, dkb + (uint64_t)(k * 128), idesc_q, (acc0 || k > 0));
+          umma_bf16(tmem_dQ, dds, desc_mn<DH>(tk, k), idesc_q, (acc0 || k > 0));
         }
         umma_commit(acc_done);
         umma_commit(kv_empty + st);
@@ -683,7 +773,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         mbar_wait(acc_done, c.t & 1);
         fence_after();
         const int64_t q_glob = (int64_t)b * S + c.tile * 128 + row;
-        store_acc_row(tmem_dQ + lane_addr, dqkv + (q_glob * h + hh) * 3 * DH);
+        store_acc_row<DH>(tmem_dQ + lane_addr, dqkv + (q_glob * h + hh) * 3 * DH);
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(out_done);
@@ -700,7 +790,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
 static int check_shape(const char* who, int B, int S, int h, int Dh) {
   NPT_REQUIRE(B > 0 && h > 0, "%s: bad shape", who);
-  NPT_REQUIRE(Dh == 64, "%s: fused attention supports head_dim 64 only (got %d); use the GEMM + softmax path", who, Dh);
+  NPT_REQUIRE(Dh == 64 || Dh == 96, "%s: fused attention supports head_dim 64 and 96 (got %d); use the GEMM + softmax path", who, Dh);
   NPT_REQUIRE(S > 0 && S % 128 == 0, "%s: fused attention needs seq_len %% 128 == 0 (got %d)", who, S);
   return 0;
 }
@@ -710,30 +800,69 @@ static int persistent_grid(int items) {
   return items < sms ? items : sms;
 }
 
+template <int DH>
+static int attention_fwd_t(const void* qkv_bf16, void* out_bf16, float* lse, int B, int S, int h, float divisor, cudaStream_t st) {
+  using C = AttnCfg<DH>;
+  CUtensorMap tm;
+  if (int rc = make_map_bf16_2d(&tm, qkv_bf16, (int64_t)h * 3 * DH, (int64_t)B * S, (int64_t)h * 3 * DH, C::CH, 128, C::CH == 64 ? 128 : 64)) return rc;
+  auto kern = attn_fwd_kernel<DH>;
+  static bool attr = false;
+  if (!attr) {
+    NPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem<DH>::TOTAL));
+    attr = true;
+  }
+  const int grid = persistent_grid(B * h * (S / 128));
+  NPT_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(AT_THREADS), AttnFwdSmem<DH>::TOTAL, st, tm,
+                            (__nv_bfloat16*)out_bf16, lse, B, S, h, 1.0f / divisor));
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int DH>
+static int attention_bwd_t(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse, void* dqkv_bf16,
+                           int B, int S, int h, float divisor, float* D, cudaStream_t st) {
+  using C = AttnCfg<DH>;
+  const int64_t rows = (int64_t)B * S * h;
+  NPT_CHECK_CUDA(launch_pdl(attn_bwd_prep_kernel<DH>, dim3((unsigned)cdiv(rows * 8, 256)), dim3(256), 0, st,
+                            (const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)d_out_bf16, D, rows, S, h));
+  NPT_LAUNCH_CHECK();
+  CUtensorMap tmQKV, tmDO;
+  const int sw = C::CH == 64 ? 128 : 64;
+  if (int rc = make_map_bf16_2d(&tmQKV, qkv_bf16, (int64_t)h * 3 * DH, (int64_t)B * S, (int64_t)h * 3 * DH, C::CH, 128, sw)) return rc;
+  if (int rc = make_map_bf16_2d(&tmDO, d_out_bf16, (int64_t)h * DH, (int64_t)B * S, (int64_t)h * DH, C::CH, 128, sw)) return rc;
+  auto kdkv = attn_bwd_dkv_kernel<DH>;
+  auto kdq = attn_bwd_dq_kernel<DH>;
+  static bool attr = false;
+  if (!attr) {
+    NPT_CHECK_CUDA(cudaFuncSetAttribute(kdkv, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDkvSmem<DH>::TOTAL));
+    NPT_CHECK_CUDA(cudaFuncSetAttribute(kdq, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem<DH>::TOTAL));
+    attr = true;
+  }
+  const int grid = persistent_grid(B * h * (S / 128));
+  const float inv_div = 1.0f / divisor;
+  NPT_CHECK_CUDA(launch_pdl(kdkv, dim3(grid), dim3(AT_THREADS), AttnDkvSmem<DH>::TOTAL, st, tmQKV, tmDO, lse, (const float*)D,
+                            (__nv_bfloat16*)dqkv_bf16, B, S, h, inv_div));
+  NPT_LAUNCH_CHECK();
+  NPT_CHECK_CUDA(launch_pdl(kdq, dim3(grid), dim3(AT_THREADS), AttnDqSmem<DH>::TOTAL, st, tmQKV, tmDO, lse, (const float*)D,
+                            (__nv_bfloat16*)dqkv_bf16, B, S, h, inv_div));
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace npt
 
 using namespace npt;
 
 extern "C" {
 
-int npt_attention_supported(int32_t S, int32_t Dh) { return (Dh == 64 && S > 0 && S % 128 == 0) ? 1 : 0; }
+int npt_attention_supported(int32_t S, int32_t Dh) { return ((Dh == 64 || Dh == 96) && S > 0 && S % 128 == 0) ? 1 : 0; }
 
 int npt_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int32_t B, int32_t S, int32_t h, int32_t Dh,
                       float divisor, void* stream) {
   if (int rc = check_shape("attention_fwd", B, S, h, Dh)) return rc;
   NPT_REQUIRE(aligned16(qkv_bf16) && aligned16(out_bf16), "attention_fwd: buffers must be 16-byte aligned");
-  CUtensorMap tm;
-  if (int rc = make_map_bf16_2d(&tm, qkv_bf16, (int64_t)h * 3 * Dh, (int64_t)B * S, (int64_t)h * 3 * Dh, 64, 128)) return rc;
-  static bool attr = false;
-  if (!attr) {
-    NPT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::TOTAL));
-    attr = true;
-  }
-  const int grid = persistent_grid(B * h * (S / 128));
-  NPT_CHECK_CUDA(launch_pdl(attn_fwd_kernel, dim3(grid), dim3(AT_THREADS), AttnFwdSmem::TOTAL, (cudaStream_t)stream, tm,
-                            (__nv_bfloat16*)out_bf16, lse, B, S, h, 1.0f / divisor));
-  NPT_LAUNCH_CHECK();
-  return 0;
+  if (Dh == 96) return attention_fwd_t<96>(qkv_bf16, out_bf16, lse, B, S, h, divisor, (cudaStream_t)stream);
+  return attention_fwd_t<64>(qkv_bf16, out_bf16, lse, B, S, h, divisor, (cudaStream_t)stream);
 }
 
 size_t npt_attention_bwd_workspace_bytes(int32_t B, int32_t S, int32_t h) { return (size_t)B * S * h * sizeof(float); }
@@ -745,30 +874,9 @@ int npt_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_
   NPT_REQUIRE(workspace && workspace_bytes >= npt_attention_bwd_workspace_bytes(B, S, h), "attention_bwd: workspace too small");
   NPT_REQUIRE(aligned16(qkv_bf16) && aligned16(out_bf16) && aligned16(d_out_bf16) && aligned16(dqkv_bf16),
               "attention_bwd: buffers must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  float* D = (float*)workspace;
-  const int64_t rows = (int64_t)B * S * h;
-  NPT_CHECK_CUDA(launch_pdl(attn_bwd_prep_kernel, dim3((unsigned)cdiv(rows * 8, 256)), dim3(256), 0, st,
-                            (const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)d_out_bf16, D, rows, S, h));
-  NPT_LAUNCH_CHECK();
-  CUtensorMap tmQKV, tmDO;
-  if (int rc = make_map_bf16_2d(&tmQKV, qkv_bf16, (int64_t)h * 3 * Dh, (int64_t)B * S, (int64_t)h * 3 * Dh, 64, 128)) return rc;
-  if (int rc = make_map_bf16_2d(&tmDO, d_out_bf16, (int64_t)h * Dh, (int64_t)B * S, (int64_t)h * Dh, 64, 128)) return rc;
-  static bool attr = false;
-  if (!attr) {
-    NPT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDkvSmem::TOTAL));
-    NPT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem::TOTAL));
-    attr = true;
-  }
-  const int grid = persistent_grid(B * h * (S / 128));
-  const float inv_div = 1.0f / divisor;
-  NPT_CHECK_CUDA(launch_pdl(attn_bwd_dkv_kernel, dim3(grid), dim3(AT_THREADS), AttnDkvSmem::TOTAL, st, tmQKV, tmDO, lse, D,
-                            (__nv_bfloat16*)dqkv_bf16, B, S, h, inv_div));
-  NPT_LAUNCH_CHECK();
-  NPT_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel, dim3(grid), dim3(AT_THREADS), AttnDqSmem::TOTAL, st, tmQKV, tmDO, lse, D,
-                            (__nv_bfloat16*)dqkv_bf16, B, S, h, inv_div));
-  NPT_LAUNCH_CHECK();
-  return 0;
+  if (Dh == 96)
+    return attention_bwd_t<96>(qkv_bf16, out_bf16, d_out_bf16, lse, dqkv_bf16, B, S, h, divisor, (float*)workspace, (cudaStream_t)stream);
+  return attention_bwd_t<64>(qkv_bf16, out_bf16, d_out_bf16, lse, dqkv_bf16, B, S, h, divisor, (float*)workspace, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -4,7 +4,7 @@
 // operand x is therefore split as x = hi + lo with hi = x & 0xffffe000 (exactly a TF32 number) and
 // lo = x - hi (exact in fp32, |lo| <= 2^-10 |x|), and the product is accumulated as
 //     A*B  ~=  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi            (the dropped A_lo*B_lo term is ~2^-20 relative)
-// three tcgen05.mma per k-step into the same fp32 TMEM accumulator.  The split is done INSIDE the kernel:
+// three tcgen05.mma per k-step into fp32 TMEM accumulators (main term and cross terms apart, added in the epilogue).  The split is done INSIDE the kernel:
 // TMA brings the raw fp32 tiles into 128B-swizzled shared memory, four "converter" warps rewrite each tile
 // in place as `hi` and write `lo` into a second tile at the same (swizzled) offsets — the transform is
 // element-wise, so the layout never has to be decoded — and only then is the stage handed to the MMA warp.
@@ -144,7 +144,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(acc_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);   // columns [0, BN): A_hi*B_hi, [BN, 2 BN): the two cross terms
   fence_before();
   __syncthreads();
   fence_after();
@@ -201,9 +201,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < TF_BK / 8; ++k) {
           const uint64_t oa = (uint64_t)(k * adv_a), ob = (uint64_t)(k * adv_b);
-          umma_tf32(tmem, a_lo + oa, b_hi + ob, idesc, (i > 0 || k > 0) ? 1u : 0u);   // small terms first
-          umma_tf32(tmem, a_hi + oa, b_lo + ob, idesc, 1u);
-          umma_tf32(tmem, a_hi + oa, b_hi + ob, idesc, 1u);
+          // The tensor core adds into the TMEM accumulator with truncation: one error of up to an ulp OF THE
+          // ACCUMULATOR per MMA.  The cross terms are 2^-11 of the main term, so they get their own accumulator
+          // (their truncation errors scale with it) and the main one sees a third of the additions.
+          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+          umma_tf32(tmem + BN, a_lo + oa, b_hi + ob, idesc, acc);
+          umma_tf32(tmem + BN, a_hi + oa, b_lo + ob, idesc, 1u);
+          umma_tf32(tmem, a_hi + oa, b_hi + ob, idesc, acc);
         }
         umma_commit(empty_bar + s);
       }
@@ -238,9 +242,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int c = 0; c < BN / 32; ++c) {
       const int nb = n0 + c * 32;
       if (nb >= p.N) break;   // warp-uniform
-      uint32_t r[32];
+      uint32_t r[32], rx[32];
       tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(BN + c * 32), rx);
       tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rx[j]));
       if (m >= p.M) continue;
       if (p.raw) {
         float* prow = partial + (((int64_t)split * p.batch + b) * p.M + m) * p.N;
@@ -266,7 +273,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     fence_after();
-    tmem_dealloc<BN>(tmem);
+    tmem_dealloc<2 * BN>(tmem);
   }
 }
 

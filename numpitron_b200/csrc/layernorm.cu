@@ -300,6 +300,167 @@ ln_bwd_warp_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Backward, bf16 inputs (the bf16 mode's step path): STREAMING variant.  The register kernel above keeps two
+// rows per warp in flight in registers (126 registers, 16 warps per SM) and issues no loads while it reduces
+// and computes: 2.6 TB/s.  Here every warp owns a ring of R row slots in shared memory that one lane fills
+// with 1-D bulk async copies (cp.async.bulk, completion on an mbarrier per slot): the loads of the next R
+// rows are always in flight, independent of what the warp is computing, and cost no registers.
+// Per-warp running sums of dx (DXSUM) stay in shared memory; the warps' dgamma / dbeta partials are added
+// into one [NSL][d] block partial in warp order (deterministic).
+__device__ __forceinline__ uint32_t ln_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ln_bulk_row(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 ln_lds_bf16x4(uint32_t addr) {
+  uint2 u;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u.x), "=r"(u.y) : "r"(addr) : "memory");
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <int NV, bool PEER, bool DXSUM>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean_in, const float* __restrict__ var_in,
+                     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy_peer,
+                     float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, float* __restrict__ partial,
+                     int64_t rows, int d, float eps, int R) {
+  constexpr int NT = PEER ? 3 : 2;       // row tensors per slot: x, dy (, the other rank's dy)
+  constexpr int NSL = DXSUM ? 3 : 2;
+  extern __shared__ __align__(16) uint8_t ln_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = d >> 2;
+  const uint32_t row_bytes = (uint32_t)d * 2;
+  // layout: [warp][R][NT][d] bf16 | [warp][d] fp32 (DXSUM) | [NSL][d] fp32 (block partial) | [warp][R] mbarriers
+  uint8_t* ring = ln_smem + (size_t)warp * R * NT * row_bytes;
+  float* dsum_base = reinterpret_cast<float*>(ln_smem + (size_t)kLnWarps * R * NT * row_bytes);
+  float4* dsum = reinterpret_cast<float4*>(dsum_base + (size_t)warp * d);
+  float* comb = dsum_base + (DXSUM ? (size_t)kLnWarps * d : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(comb + (size_t)NSL * d) + warp * R;
+  if (lane == 0)
+    for (int s2 = 0; s2 < R; ++s2)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ln_smem_u32(bars + s2)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  if (DXSUM) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + i * 32 < nvec) dsum[lane + i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4 g[NV], ag[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    g[i] = (c < nvec) ? __ldg(g4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  pdl_wait();  // programmatic dependent launch: everything above is private set-up
+  pdl_trigger();
+  const int64_t stride = (int64_t)gridDim.x * kLnWarps;
+  const int64_t first = (int64_t)blockIdx.x * kLnWarps + warp;
+  auto issue = [&](int slot, int64_t row) {   // lane 0 only
+    const uint32_t bar = ln_smem_u32(bars + slot);
+    const uint32_t dst = ln_smem_u32(ring + (size_t)slot * NT * row_bytes);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(NT * row_bytes) : "memory");
+    ln_bulk_row(dst, x + row * d, row_bytes, bar);
+    ln_bulk_row(dst + row_bytes, dy + row * d, row_bytes, bar);
+    if (PEER) ln_bulk_row(dst + 2 * row_bytes, dy_peer + row * d, row_bytes, bar);
+  };
+  if (lane == 0)
+    for (int s2 = 0; s2 < R; ++s2)
+      if (first + s2 * stride < rows) issue(s2, first + s2 * stride);
+  const float inv_d = 1.0f / (float)d;
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t row = first; row < rows; row += stride) {
+    const float mean = mean_in[row], var = var_in[row];
+    const float rden = __frcp_rn(sqrtf(var + eps)), rstd = __frcp_rn(sqrtf(var));  // std without eps (normalization.py:48-50)
+    {  // wait for this slot's bytes
+      const uint32_t bar = ln_smem_u32(bars + slot);
+      uint32_t done;
+      do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+      } while (!done);
+    }
+    const uint32_t base = ln_smem_u32(ring + (size_t)slot * NT * row_bytes);
+    float4 xh[NV], w[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        float4 xv = ln_lds_bf16x4(base + c * 8);
+        float4 dd = ln_lds_bf16x4(base + row_bytes + c * 8);
+        if (PEER) {
+          const float4 pp = ln_lds_bf16x4(base + 2 * row_bytes + c * 8);
+          dd.x = __bfloat162float(__float2bfloat16_rn(dd.x + pp.x)); dd.y = __bfloat162float(__float2bfloat16_rn(dd.y + pp.y));
+          dd.z = __bfloat162float(__float2bfloat16_rn(dd.z + pp.z)); dd.w = __bfloat162float(__float2bfloat16_rn(dd.w + pp.w));
+        }
+        xv.x = (xv.x - mean) * rden; xv.y = (xv.y - mean) * rden; xv.z = (xv.z - mean) * rden; xv.w = (xv.w - mean) * rden;
+        ag[i].x += dd.x * xv.x; ag[i].y += dd.y * xv.y; ag[i].z += dd.z * xv.z; ag[i].w += dd.w * xv.w;
+        ab[i].x += dd.x; ab[i].y += dd.y; ab[i].z += dd.z; ab[i].w += dd.w;
+        const float4 gv = g[i];
+        dd.x *= gv.x; dd.y *= gv.y; dd.z *= gv.z; dd.w *= gv.w;   // gamma * dy
+        s1 += (xv.x * dd.x + xv.y * dd.y) + (xv.z * dd.z + xv.w * dd.w);
+        s2 += (dd.x + dd.y) + (dd.z + dd.w);
+        xh[i] = xv; w[i] = dd;
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+    // every lane's shared-memory reads fed the shuffles above: the slot can be refilled
+    if (lane == 0 && row + (int64_t)R * stride < rows) issue(slot, row + (int64_t)R * stride);
+    if (++slot == R) { slot = 0; phase ^= 1; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        float4 o;
+        o.x = (w[i].x - c1 * xh[i].x - c2) * rstd;
+        o.y = (w[i].y - c1 * xh[i].y - c2) * rstd;
+        o.z = (w[i].z - c1 * xh[i].z - c2) * rstd;
+        o.w = (w[i].w - c1 * xh[i].w - c2) * rstd;
+        if (dx) st_stream(reinterpret_cast<float4*>(dx + row * d) + c, o);
+        if (dxb) st_bf16x4(dxb + row * d + (int64_t)c * 4, o);
+        if (DXSUM) {
+          float4 t = dsum[c];
+          t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+          dsum[c] = t;
+        }
+      }
+    }
+  }
+  // block partial = sum over the warps, in warp order
+  for (int w2 = 0; w2 < kLnWarps; ++w2) {
+    if (warp == w2) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + i * 32;
+        if (c < nvec) {
+          float4* cg = reinterpret_cast<float4*>(comb) + c;
+          float4* cb = reinterpret_cast<float4*>(comb + d) + c;
+          float4 a = ag[i], b = ab[i];
+          if (w2 > 0) { const float4 pa = *cg, pb = *cb; a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w; b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w; }
+          *cg = a; *cb = b;
+          if (DXSUM) {
+            float4* cs = reinterpret_cast<float4*>(comb + 2 * d) + c;
+            float4 t = dsum[c];
+            if (w2 > 0) { const float4 ps = *cs; t.x += ps.x; t.y += ps.y; t.z += ps.z; t.w += ps.w; }
+            *cs = t;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < NSL * d; c += blockDim.x) partial[(size_t)blockIdx.x * NSL * d + c] = comb[c];
+}
+
 // Any d: block per row-group, scalar loops.  partial layout identical.
 __global__ void __launch_bounds__(256)
 ln_bwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
@@ -364,6 +525,12 @@ reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ ou
   }
 }
 
+static bool ln_bwd_force_register() {   // NUMPITRON_LN_BWD=register: the register-resident kernel (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NUMPITRON_LN_BWD"); v = (e && e[0] == 'r') ? 1 : 0; }
+  return v == 1;
+}
+
 static int ln_bwd_blocks(int64_t rows) {
   int64_t want = cdiv(rows, 2 * kLnWarps);
   int64_t cap = (int64_t)sm_count() * 2;
@@ -401,6 +568,49 @@ static int launch_bwd_k(const void* x, const float* g, const float* mean, const 
                             (__nv_bfloat16*)dxb, partial, rows, d, eps));
   NPT_LAUNCH_CHECK();
   return 0;
+}
+
+static size_t ln_stream_smem(int d, int R, bool peer, bool dxsum) {
+  return (size_t)kLnWarps * R * (peer ? 3 : 2) * d * 2 + (dxsum ? (size_t)kLnWarps * d * 4 : 0) + (size_t)(dxsum ? 3 : 2) * d * 4 +
+         (size_t)kLnWarps * R * 8;
+}
+static int ln_stream_slots(int d, bool peer) {
+  // about 6 KB of rows in flight per warp (48 KB per block), at least 2 slots
+  const int per = (peer ? 3 : 2) * d * 2;
+  int R = 6144 / per;
+  return R < 2 ? 2 : (R > 6 ? 6 : R);
+}
+
+template <int NV, bool PEER, bool DXSUM>
+static int launch_bwd_stream_k(const void* x, const float* g, const float* mean, const float* var, const void* dy, const void* dyp,
+                               float* dx, void* dxb, float* partial, int* nblocks, int64_t rows, int d, float eps, cudaStream_t st) {
+  const int R = ln_stream_slots(d, PEER);
+  const size_t smem = ln_stream_smem(d, R, PEER, DXSUM);
+  auto kern = ln_bwd_stream_kernel<NV, PEER, DXSUM>;
+  static int per_sm = 0;
+  static size_t per_sm_smem = 0;
+  if (per_sm == 0 || per_sm_smem != smem) {
+    NPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NPT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLnWarps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    per_sm_smem = smem;
+  }
+  int64_t want = cdiv(rows, kLnWarps);
+  const int64_t cap = (int64_t)sm_count() * (per_sm > 2 ? 2 : per_sm);   // the partial workspace holds 2 blocks per SM
+  *nblocks = (int)(want < cap ? want : cap);
+  NPT_CHECK_CUDA(launch_pdl(kern, dim3(*nblocks), dim3(kLnWarps * 32), smem, st, (const __nv_bfloat16*)x, g, mean, var,
+                            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dyp, dx, (__nv_bfloat16*)dxb, partial, rows, d, eps, R));
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int NV>
+static int launch_bwd_stream(const void* x, const float* g, const float* mean, const float* var, const void* dy, const void* dyp,
+                             float* dx, void* dxb, float* partial, bool dxsum, int* nblocks, int64_t rows, int d, float eps, cudaStream_t st) {
+  if (dyp) return dxsum ? launch_bwd_stream_k<NV, true, true>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st)
+                        : launch_bwd_stream_k<NV, true, false>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st);
+  return dxsum ? launch_bwd_stream_k<NV, false, true>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st)
+               : launch_bwd_stream_k<NV, false, false>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st);
 }
 
 template <int NV>
@@ -498,7 +708,20 @@ int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16,
   NPT_REQUIRE(!dy_peer || (ib && aligned8(dy_peer)), "layernorm_bwd: a peer partial needs bf16 inputs and an 8-byte aligned buffer");
   NPT_REQUIRE(!(dxsum || ib) || vec,
               "layernorm_bwd: fused dx column sums / bf16 inputs need d %% 4 == 0, d <= %d and aligned buffers", kLnMaxVec * 128);
-  if (vec) {
+  const bool stream_ok = vec && ib && d % 8 == 0 && aligned16(x) && aligned16(dy) && (!dy_peer || aligned16(dy_peer)) && !ln_bwd_force_register();
+  if (stream_ok) {
+    const int nv = (int)cdiv(d, 128);
+    int rc;
+    switch (nv) {
+      case 1: rc = launch_bwd_stream<1>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, st); break;
+      case 2: rc = launch_bwd_stream<2>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, st); break;
+      case 3: rc = launch_bwd_stream<3>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, st); break;
+      case 4: rc = launch_bwd_stream<4>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, st); break;
+      case 5: case 6: rc = launch_bwd_stream<6>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, st); break;
+      default: rc = launch_bwd_stream<8>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, st); break;
+    }
+    if (rc) return rc;
+  } else if (vec) {
     nblocks = ln_bwd_blocks(rows);
     const int nv = (int)cdiv(d, 128);
     int rc;

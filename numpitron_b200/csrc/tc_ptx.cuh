@@ -89,6 +89,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
+// Same with an explicit layout type: 2 = SWIZZLE_128B (rows of 128 B, 8-row group pitch 1024 B),
+// 4 = SWIZZLE_64B (rows of 64 B, 8-row group pitch 512 B), 6 = SWIZZLE_32B.
+__device__ __forceinline__ uint64_t make_smem_desc_l(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M=128.
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
@@ -114,9 +125,9 @@ inline EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D bf16 map (rows x inner, row pitch ld elements) presented as 4-D {inner, rows, 1, 1}, SWIZZLE_128B.
+// 2-D bf16 map (rows x inner, row pitch ld elements) presented as 4-D {inner, rows, 1, 1}, SWIZZLE_128B / _64B.
 inline int make_map_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t ld, int box_inner,
-                            int box_rows) {
+                            int box_rows, int swizzle_bytes = 128) {
   EncodeTiledFn enc = get_encode();
   NPT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, 1, 1};
@@ -125,8 +136,8 @@ inline int make_map_bf16_2d(CUtensorMap* map, const void* base, int64_t inner, i
   cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NPT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
 }

@@ -270,11 +270,14 @@ def test_gemm_batched_head_layout(mode):
 @pytest.mark.parametrize("B,S,h", [(1, 128, 1), (2, 256, 3), (1, 512, 2), (3, 256, 6),
                                    (40, 256, 6),     # 480 work items: every persistent CTA walks several
                                    (50, 128, 4),     # 200 single-step items
-                                   (13, 384, 5)])    # 195 items of 1-3 steps
-def test_fused_attention_fwd_bwd(B, S, h):
+                                   (13, 384, 5),     # 195 items of 1-3 steps
+                                   (2, 1024, 1)])    # GPT-2 small under tp = 8: one local head, 8 key tiles
+@pytest.mark.parametrize("Dh", [64, 96])
+def test_fused_attention_fwd_bwd(B, S, h, Dh):
     """Flash-style tcgen05 attention against the reference's arithmetic (attention.py:43-52, 81-98)
-    evaluated in fp64 on the same bf16-rounded inputs; scale = 1/sqrt(d_model) with d_model = 384."""
-    Dh, div = 64, float(np.float32(384**0.5))
+    evaluated in fp64 on the same bf16-rounded inputs; scale = 1/sqrt(d_model) with d_model = 384.
+    head_dim 96 = BASELINE configs[2] (12 heads of 64 re-cut as 1 local head of 96 per rank, attention.py:37-45)."""
+    div = float(np.float32(384**0.5))
     rng = np.random.default_rng(S + h)
     qkv = bf16_round(rng.standard_normal((B, S, h, 3, Dh)) * 2.0)
     d_out = bf16_round(rng.standard_normal((B, S, h, Dh)))
@@ -603,5 +606,5 @@ def test_errors_are_reported_not_swallowed():
         ops.gemm(a, a, 128, 60, 64, lda=64, ldb=60, C_out=rt.empty((128, 60)), ldc=60, mode=1)  # ldb % 8 != 0
     with pytest.raises(TypeError):
         ops.gemm(a, a, 128, 64, 64, lda=64, ldb=64, C_out=rt.empty((128, 64)), ldc=64, mode=0)  # bf16 into the fp32 kernel
-    with pytest.raises(NptError, match="head_dim 64"):
-        ops.attention_fwd(rt.empty((1, 128, 3 * 96), torch.bfloat16), 1, 128, 1, 96, 10.0)
+    with pytest.raises(NptError, match="head_dim 64 and 96"):
+        ops.attention_fwd(rt.empty((1, 128, 3 * 80), torch.bfloat16), 1, 128, 1, 80, 10.0)
