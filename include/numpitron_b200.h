@@ -146,6 +146,18 @@ int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16,
                          const float* gamma, const float* mean, const float* var, float* dx,
                          void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int64_t rows,
                          int32_t d, float eps, void* workspace, size_t workspace_bytes, void* stream);
+/* v3 = v2 plus: `n_partials` (host pointer, may be NULL) receives the number of per-block partials the first
+ * stage left in `workspace`, laid out [n_partials][2 or 3][d] (dgamma, dbeta, and dx_colsum when requested).
+ * defer_reduce != 0: the second stage is skipped and dgamma / dbeta / dx_colsum are not written; the caller
+ * keeps `workspace` alive and hands the partials to npt_adam_step (npt_adam_tensor.g_splits = n_partials,
+ * g_split_stride = (2 or 3) * d), which adds them in block order — the additions of the second stage, so the
+ * parameter update is bit-identical (these gradients, nn/normalization.py:38-45 and nn/linear.py:57-58, are
+ * only ever read by the optimizer). */
+int npt_layernorm_bwd_v3(const void* x, const void* dy, int32_t inputs_are_bf16, const void* dy_peer,
+                         const float* gamma, const float* mean, const float* var, float* dx,
+                         void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int64_t rows,
+                         int32_t d, float eps, void* workspace, size_t workspace_bytes,
+                         int32_t defer_reduce, int32_t* n_partials, void* stream);
 
 /* ---- ReLU — nn/activation.py:38-43 (stand-alone; the GEMM epilogue fuses both) ---------- */
 int npt_relu_fwd(const float* x, float* y, void* y_bf16, int64_t n, void* stream);

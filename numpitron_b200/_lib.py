@@ -73,6 +73,8 @@ _SIGNATURES = {
     "npt_layernorm_bf16_input_supported": (c_int, [c_int32]),
     "npt_layernorm_fwd_v2": (c_int, [_P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P]),
     "npt_layernorm_bwd_v2": (c_int, [_P, _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P, c_size_t, _P]),
+    "npt_layernorm_bwd_v3": (c_int, [_P, _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P, c_size_t,
+                                     c_int32, _P, _P]),
     "npt_relu_fwd": (c_int, [_P, _P, _P, c_int64, _P]),
     "npt_relu_bwd": (c_int, [_P, _P, _P, _P, c_int64, _P]),
     "npt_colsum_workspace_bytes": (c_size_t, [c_int64, c_int32]),

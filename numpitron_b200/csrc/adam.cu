@@ -35,13 +35,12 @@ __device__ __forceinline__ float4 adam_grad4(const npt_adam_tensor& t, int64_t i
   const float4* g0 = reinterpret_cast<const float4*>(t.g) + i4;
   const int64_t st4 = t.g_split_stride >> 2;  // the vector path requires a stride that is a multiple of 4
   int64_t s = 0;
-  for (; s + 4 <= t.g_splits; s += 4) {  // four independent loads in flight, additions in split order
-    const float4 a0 = ld_stream(g0 + s * st4), a1 = ld_stream(g0 + (s + 1) * st4);
-    const float4 a2 = ld_stream(g0 + (s + 2) * st4), a3 = ld_stream(g0 + (s + 3) * st4);
-    acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;
-    acc.x += a1.x; acc.y += a1.y; acc.z += a1.z; acc.w += a1.w;
-    acc.x += a2.x; acc.y += a2.y; acc.z += a2.z; acc.w += a2.w;
-    acc.x += a3.x; acc.y += a3.y; acc.z += a3.z; acc.w += a3.w;
+  for (; s + 8 <= t.g_splits; s += 8) {  // eight independent loads in flight, additions in split order
+    float4 a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = ld_stream(g0 + (s + k) * st4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc.x += a[k].x; acc.y += a[k].y; acc.z += a[k].z; acc.w += a[k].w; }
   }
   for (; s < t.g_splits; ++s) {
     const float4 a = ld_stream(g0 + s * st4);

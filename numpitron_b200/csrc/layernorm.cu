@@ -501,31 +501,32 @@ ln_bwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma
   }
 }
 
-// Stage 2: out[c] = sum_b partial[b][c]   (fixed order -> deterministic)
-// 32 columns x 32 row-lanes per block: every lane sums a strided subset of the partial rows
-// (independent loads in flight), then a fixed-order smem tree adds the 32 lanes.
-__global__ void __launch_bounds__(1024)
+// Stage 2: out[c] = ((0 + partial[0][c]) + partial[1][c]) + ...  — block order, one thread per column, eight
+// loads in flight.  The same additions in the same order as the fused Adam kernel performs when the partials
+// are handed to it un-reduced (npt_adam_tensor.g_splits), so both routes give identical bits.
+__global__ void __launch_bounds__(128)
 reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out0,
                        float* __restrict__ out1, float* __restrict__ out2, int nsl, int nblocks, int d) {
   pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
   pdl_trigger();
-  __shared__ float sm[32][33];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
-  float t = 0.f;
-  if (c < nsl * d)
-    for (int b = ry; b < nblocks; b += 32) t += partial[(size_t)b * nsl * d + c];
-  sm[ry][cx] = t;
-  __syncthreads();
-  if (ry == 0 && c < nsl * d) {
-    float s = 0.f;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nsl * d) return;
+  const size_t pitch = (size_t)nsl * d;
+  const float* src = partial + c;
+  float acc = 0.f;
+  int b = 0;
+  for (; b + 8 <= nblocks; b += 8) {
+    float v[8];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) s += sm[k][cx];
-    if (c < d) out0[c] = s; else if (c < 2 * d) out1[c - d] = s; else out2[c - 2 * d] = s;
+    for (int k = 0; k < 8; ++k) v[k] = src[(size_t)(b + k) * pitch];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += v[k];
   }
+  for (; b < nblocks; ++b) acc += src[(size_t)b * pitch];
+  if (c < d) out0[c] = acc; else if (c < 2 * d) out1[c - d] = acc; else out2[c - 2 * d] = acc;
 }
 
-static bool ln_bwd_force_register() {   // NUMPITRON_LN_BWD=register: the register-resident kernel (A/B measurements)
+static bool ln_bwd_force_register() {   // NUMPITRON_LN_BWD=register: the register-resident kernel at every width (A/B measurements)
   static int v = -1;
   if (v < 0) { const char* e = getenv("NUMPITRON_LN_BWD"); v = (e && e[0] == 'r') ? 1 : 0; }
   return v == 1;
@@ -692,6 +693,14 @@ int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16,
                          const float* var, float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum,
                          int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
                          void* stream) {
+  return npt_layernorm_bwd_v3(x, dy, inputs_are_bf16, dy_peer, gamma, mean, var, dx, dx_bf16, dgamma, dbeta, dx_colsum, rows, d, eps,
+                              workspace, workspace_bytes, 0, nullptr, stream);
+}
+
+int npt_layernorm_bwd_v3(const void* x, const void* dy, int32_t inputs_are_bf16, const void* dy_peer, const float* gamma, const float* mean,
+                         const float* var, float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum,
+                         int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
+                         int32_t defer_reduce, int32_t* n_partials, void* stream) {
   NPT_REQUIRE(rows > 0 && d > 0, "layernorm_bwd: bad shape rows=%lld d=%d", (long long)rows, d);
   NPT_REQUIRE(dx || dx_bf16, "layernorm_bwd: no output");
   NPT_REQUIRE(workspace && workspace_bytes >= npt_layernorm_bwd_workspace_bytes(rows, d),
@@ -708,7 +717,9 @@ int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16,
   NPT_REQUIRE(!dy_peer || (ib && aligned8(dy_peer)), "layernorm_bwd: a peer partial needs bf16 inputs and an 8-byte aligned buffer");
   NPT_REQUIRE(!(dxsum || ib) || vec,
               "layernorm_bwd: fused dx column sums / bf16 inputs need d %% 4 == 0, d <= %d and aligned buffers", kLnMaxVec * 128);
-  const bool stream_ok = vec && ib && d % 8 == 0 && aligned16(x) && aligned16(dy) && (!dy_peer || aligned16(dy_peer)) && !ln_bwd_force_register();
+  // measured (benchmarks/kernbench.py): rows of <= 512 columns fit the register kernel's two-rows-in-flight scheme
+  // (18 us vs 22 us at 16384 x 384); wider rows run 1.6-2x faster on the streaming kernel (32768 x 768: 76 us vs 145 us)
+  const bool stream_ok = vec && ib && d > 512 && d % 8 == 0 && aligned16(x) && aligned16(dy) && (!dy_peer || aligned16(dy_peer)) && !ln_bwd_force_register();
   if (stream_ok) {
     const int nv = (int)cdiv(d, 128);
     int rc;
@@ -742,7 +753,9 @@ int npt_layernorm_bwd_v2(const void* x, const void* dy, int32_t inputs_are_bf16,
     NPT_LAUNCH_CHECK();
   }
   const int nsl = dxsum ? 3 : 2;
-  NPT_CHECK_CUDA(launch_pdl(reduce_partials_kernel, dim3((unsigned)cdiv(nsl * (int64_t)d, 32)), dim3(1024), 0, st, partial,
+  if (n_partials) *n_partials = nblocks;
+  if (defer_reduce) return 0;   // the caller hands partial[nblocks][nsl][d] to Adam (g_splits = nblocks, stride nsl * d)
+  NPT_CHECK_CUDA(launch_pdl(reduce_partials_kernel, dim3((unsigned)cdiv(nsl * (int64_t)d, 128)), dim3(128), 0, st, partial,
                             dgamma, dbeta, dx_colsum, nsl, nblocks, d));
   NPT_LAUNCH_CHECK();
   return 0;

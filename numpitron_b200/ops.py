@@ -170,10 +170,8 @@ def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False, bf16_only=False
     rows = x.numel() // d
     dx = None if bf16_only else rt.empty(x.shape)
     dxb = rt.empty(x.shape, _BF16) if (want_bf16 or bf16_only) else None
-    dgamma, dbeta = rt.empty((d,)), rt.empty((d,))
-    colsum_out = rt.empty((d,)) if (want_colsum and lib.npt_layernorm_bwd_colsum_supported(d)) else None
+    want_cs = bool(want_colsum and lib.npt_layernorm_bwd_colsum_supported(d))
     need = lib.npt_layernorm_bwd_workspace_bytes(rows, d)
-    ws = rt.workspace(need)
     # x (the saved LayerNorm input) and dy are read as one dtype: both bf16 when either is
     in_bf16 = x.dtype == _BF16 or dy.dtype == _BF16
     if in_bf16 and x.dtype != _BF16:
@@ -181,10 +179,33 @@ def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False, bf16_only=False
     if in_bf16 and dy.dtype != _BF16:
         dy = cast_bf16(dy)
     assert not dy_peer or in_bf16
+    # Inside GraphedTrainStep nothing but Adam reads dgamma / dbeta / the bias gradient: the per-block partials
+    # go to it un-reduced (one launch less per LayerNorm; same additions in the same order).
+    defer = rt.defer_wgrad()
+    if defer:
+        ws = rt.empty((need,), torch.uint8)   # lives until the optimizer step
+        dgamma = dbeta = colsum_out = None
+    else:
+        ws = rt.workspace(need)
+        dgamma, dbeta = rt.empty((d,)), rt.empty((d,))
+        colsum_out = rt.empty((d,)) if want_cs else None
+    n_part = C.c_int32(0)
     with _timed("layernorm_bwd", "hbm", _nbytes(x, dy, dx, dxb, mean, var) + (_nbytes(dy) if dy_peer else 0)):
-        check(lib.npt_layernorm_bwd_v2(_p(x), _p(dy), int(in_bf16), dy_peer or None, _p(gamma), _p(mean), _p(var), _p(dx), _p(dxb),
-                                       _p(dgamma), _p(dbeta), _p(colsum_out), rows, d, eps, ws.data_ptr(), ws.numel(),
-                                       rt.stream()), "npt_layernorm_bwd_v2")
+        check(lib.npt_layernorm_bwd_v3(_p(x), _p(dy), int(in_bf16), dy_peer or None, _p(gamma), _p(mean), _p(var), _p(dx), _p(dxb),
+                                       _p(dgamma), _p(dbeta), (_p(ws) if want_cs else None) if defer else _p(colsum_out),  # non-NULL = wanted
+                                       rows, d, eps, ws.data_ptr(), ws.numel(),
+                                       int(defer), C.addressof(n_part) if defer else None, rt.stream()), "npt_layernorm_bwd_v3")
+    if defer:
+        nsl, n = (3 if want_cs else 2), int(n_part.value)
+        part = ws.view(torch.float32)
+
+        def slice_(k):   # partial[:, k, :] as a stack of n split partials, pitch nsl * d
+            t = part.as_strided((n, d), (nsl * d, 1), k * d)
+            t._npt_splits, t._npt_split_stride, t._npt_keep = n, nsl * d, ws
+            return t
+
+        dgamma, dbeta = slice_(0), slice_(1)
+        colsum_out = slice_(2) if want_cs else None
     out = dxb if bf16_only else dx
     if not bf16_only and dxb is not None:
         rt.attach_bf16(dx, dxb)
@@ -445,7 +466,8 @@ class AdamTable:
 
     def fill(self, entries):
         """entries: list of (p, g, m, v, shadow_or_None).  Re-uploads only when a pointer changed."""
-        key = tuple((_p(p), _p(g), _p(m), _p(v), _p(sh), getattr(g, "_npt_splits", 1), p.numel()) for p, g, m, v, sh in entries)
+        key = tuple((_p(p), _p(g), _p(m), _p(v), _p(sh), getattr(g, "_npt_splits", 1), getattr(g, "_npt_split_stride", 0), p.numel())
+                    for p, g, m, v, sh in entries)
         if key == self.key:
             return
         assert len(entries) <= self.capacity
@@ -457,7 +479,7 @@ class AdamTable:
             t.p, t.g, t.m, t.v = _p(p), _p(g), _p(m), _p(v)
             t.n = p.numel()
             t.g_splits = getattr(g, "_npt_splits", 1)   # split-K partials left by a weight-gradient GEMM
-            t.g_split_stride = p.numel()
+            t.g_split_stride = getattr(g, "_npt_split_stride", p.numel())   # LayerNorm block partials: pitch (2 or 3) * d
             if sh is not None:
                 t.p_bf16 = _p(sh)
                 t.shadow_cols = p.shape[-1]

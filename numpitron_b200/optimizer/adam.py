@@ -78,7 +78,9 @@ class Adam:
         entries = []
         for lyr, name, state in todo:
             p = lyr.parameters[name]
-            g = p.gradient if p.gradient.is_contiguous() else p.gradient.contiguous()
+            g = p.gradient
+            if not g.is_contiguous() and not hasattr(g, "_npt_split_stride"):   # (strided stacks of partials are read in place)
+                g = g.contiguous()
             shadow = lyr._shadows.get(name) if rt.is_bf16() else None
             entries.append((p.data, g, state.momentum.data, state.velocity.data, shadow))
         table = self._table_for(entries)
@@ -100,8 +102,8 @@ class Adam:
 
         # the gradient may be a stack of split-K partials at the address an earlier plain gradient had: the
         # split count and the element count are part of the identity of an entry
-        key = tuple((rt.ptr(a), rt.ptr(b), rt.ptr(c), rt.ptr(d), rt.ptr(e), getattr(b, "_npt_splits", 1), a.numel())
-                    for a, b, c, d, e in entries)
+        key = tuple((rt.ptr(a), rt.ptr(b), rt.ptr(c), rt.ptr(d), rt.ptr(e), getattr(b, "_npt_splits", 1),
+                     getattr(b, "_npt_split_stride", 0), a.numel()) for a, b, c, d, e in entries)
         cap = max(len(entries), self._count_parameters())
         capturing = torch.cuda.is_current_stream_capturing()
         if not capturing:
