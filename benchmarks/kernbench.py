@@ -36,7 +36,8 @@ SHAPES = {"c1": dict(T=16384, d=384, V=65, h=6, Dh=64, S=256, B=64),
 _flush = None
 
 
-def timeit(fn, iters=10, flush=True):
+def timeit(fn, iters=10, flush=True, reps=1):
+    """`reps` > 1: that many back-to-back launches per timed region (launch queue kept full), time per launch."""
     global _flush
     if _flush is None:
         _flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -49,11 +50,36 @@ def timeit(fn, iters=10, flush=True):
             _flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(reps):
+            fn()
         e1.record()
         torch.cuda.synchronize()
         total += e0.elapsed_time(e1)
-    return total / iters * 1e-3
+    return total / iters / reps * 1e-3
+
+
+def timeit_graph(fn, reps=20, iters=5):
+    """`reps` launches captured into one CUDA graph (programmatic dependent launch edges kept, no host
+    overhead between launches), replayed `iters` times: time per launch as it is inside the step's graph."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn()
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        s.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            g.replay()
+        e1.record()
+        s.synchronize()
+    return e0.elapsed_time(e1) / iters / reps * 1e-3
 
 
 def emit(op, shape, s, flops=None, bytes_=None, **extra):
@@ -120,10 +146,26 @@ def attn(sh, name):
     out, lse = ops.attention_fwd(qkv, B, S, h, Dh, div)
     causal = 0.5 * (1 + 128 / S)
     f = 4.0 * B * h * S * S * Dh * causal
-    s = timeit(lambda: ops.attention_fwd(qkv, B, S, h, Dh, div), flush=False)
+    s = timeit_graph(lambda: ops.attention_fwd(qkv, B, S, h, Dh, div))
     emit("attention_fwd", name, s, flops=f, note="causal tiles only")
-    s = timeit(lambda: ops.attention_bwd(qkv, out, do, lse, B, S, h, Dh, div), flush=False)
+    s = timeit_graph(lambda: ops.attention_bwd(qkv, out, do, lse, B, S, h, Dh, div))
     emit("attention_bwd", name, s, flops=2.5 * f, note="5 algorithmic tile GEMMs, causal tiles only")
+
+
+def gemm(sh, name):
+    """The twelve Linear GEMMs of one transformer block (forward NN, dX NT, dW TN), bf16 in / bf16 out."""
+    T, d = sh["T"], sh["d"]
+    for M, N, K, ta, tb, what in [(T, 3 * d, d, 0, 0, "qkv fwd"), (T, d, d, 0, 0, "out fwd"), (T, 4 * d, d, 0, 0, "up fwd"),
+                                  (T, d, 4 * d, 0, 0, "down fwd"), (T, d, 3 * d, 0, 1, "qkv dX"), (T, d, d, 0, 1, "out dX"),
+                                  (T, d, 4 * d, 0, 1, "up dX"), (T, 4 * d, d, 0, 1, "down dX"), (d, 3 * d, T, 1, 0, "qkv dW"),
+                                  (d, d, T, 1, 0, "out dW"), (d, 4 * d, T, 1, 0, "up dW"), (4 * d, d, T, 1, 0, "down dW")]:
+        a = torch.randn((K, M) if ta else (M, K), device="cuda").to(BF16)
+        b = torch.randn((N, K) if tb else (K, N), device="cuda").to(BF16)
+        dw = what.endswith("dW")
+        c = rt.empty((M, N)) if dw else rt.empty((M, N), BF16)
+        kw = dict(C_out=c, ldc=N) if dw else dict(Cb_out=c, ldcb=N)
+        s = timeit_graph(lambda: ops.gemm(a, b, M, N, K, lda=a.shape[1], ldb=b.shape[1], trans_a=bool(ta), trans_b=bool(tb), mode=1, **kw))
+        emit(f"gemm {what} {M}x{N}x{K}", name, s, flops=2.0 * M * N * K, timing="20 launches in one CUDA graph, operands L2-warm")
 
 
 def main():
@@ -132,7 +174,7 @@ def main():
     ap.add_argument("--shape", default="c1,c3,c3tp1,c4")
     a = ap.parse_args()
     rt.set_precision("bf16")
-    fns = {"ln": ln, "ce": ce, "emb": emb, "colsum": colsum, "attn": attn}
+    fns = {"ln": ln, "ce": ce, "emb": emb, "colsum": colsum, "attn": attn, "gemm": gemm}
     for name in a.shape.split(","):
         for k in a.only.split(","):
             fns[k](SHAPES[name], name)

@@ -141,7 +141,9 @@ static TcConfig tc_config(const npt_gemm_args& a) {
   const int sms = sm_count();
   // measured (profiles/README.md): pairs win from N ~ 1024 up (16384x1536x384: 24.3 vs 26.8 us, 8192^3: 756 vs
   // 925 us) and lose on narrow outputs, where a launch is a couple of tiles per CTA and fixed costs dominate
-  if (a.N < 1024 || m_tiles % 2 != 0 || !tc_fast_ok(a)) return best;
+  static int min_n = -1;
+  if (min_n < 0) { const char* e = getenv("NUMPITRON_GEMM_PAIR_MINN"); min_n = e ? atoi(e) : 1024; }
+  if (a.N < min_n || m_tiles % 2 != 0 || !tc_fast_ok(a)) return best;
   if (a.relu_bits_out) return best;  // bias + ReLU + bit packing: the pair's epilogue becomes the limit (27.8 vs 25.7 us)
   if (m_tiles * cdiv(a.N, best.bn) * a.batch * 2 <= sms) return best;  // split-K territory: single CTAs
   const char* env = getenv("NUMPITRON_GEMM_PAIR");

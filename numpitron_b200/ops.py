@@ -116,7 +116,7 @@ def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_of
             ws = rt.workspace(need)
             g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
     with _timed("gemm", "tensor", 2.0 * M * N * K * batch, M=M, N=N, K=K, batch=batch,
-                trans=(int(trans_a), int(trans_b)), mode=mode, splitk=bool(need)):
+                trans=(int(trans_a), int(trans_b)), mode=mode, splitk=bool(need), args=g):
         check(lib.npt_gemm(C.byref(g), rt.stream()), "npt_gemm")
     return partials
 
