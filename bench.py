@@ -344,9 +344,12 @@ def profile_eager_step(step, model, opt, batch, ms_per_step, precision):
                 ops.check(lib.npt_gemm(C.byref(p["args"]), torch.cuda.current_stream().cuda_stream), "npt_gemm")
         replay_gemms()
         step.stream.synchronize()
+        # capture_begin / capture_end directly: the torch.cuda.graph context empties the caching allocator first,
+        # which would unmap the (already released, still cached) buffers these launches point at
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=step.stream):
-            replay_gemms()
+        graph.capture_begin()
+        replay_gemms()
+        graph.capture_end()
         graph.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_rep = 5

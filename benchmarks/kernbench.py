@@ -30,6 +30,7 @@ TENSOR = PEAKS.get("bf16_tflops", 1650.2)
 BF16 = torch.bfloat16
 # rows = tokens per step per GPU at the bench batch; (d, V_local, heads, head_dim, seq)
 SHAPES = {"c1": dict(T=16384, d=384, V=65, h=6, Dh=64, S=256, B=64),
+          "c1tp2": dict(T=32768, d=384, V=33, h=3, Dh=64, S=256, B=128, tp=2),   # tp2 rank of the N >= 2 bench partition
           "c3": dict(T=32768, d=768, V=6283, h=1, Dh=96, S=1024, B=32),      # tp = 8 rank
           "c3tp1": dict(T=8192, d=768, V=50257, h=12, Dh=64, S=1024, B=8),
           "c4": dict(T=16384, d=1024, V=25129, h=8, Dh=64, S=1024, B=16)}    # tp2 x dp4 rank
@@ -153,12 +154,14 @@ def attn(sh, name):
 
 
 def gemm(sh, name):
-    """The twelve Linear GEMMs of one transformer block (forward NN, dX NT, dW TN), bf16 in / bf16 out."""
-    T, d = sh["T"], sh["d"]
-    for M, N, K, ta, tb, what in [(T, 3 * d, d, 0, 0, "qkv fwd"), (T, d, d, 0, 0, "out fwd"), (T, 4 * d, d, 0, 0, "up fwd"),
-                                  (T, d, 4 * d, 0, 0, "down fwd"), (T, d, 3 * d, 0, 1, "qkv dX"), (T, d, d, 0, 1, "out dX"),
-                                  (T, d, 4 * d, 0, 1, "up dX"), (T, 4 * d, d, 0, 1, "down dX"), (d, 3 * d, T, 1, 0, "qkv dW"),
-                                  (d, d, T, 1, 0, "out dW"), (d, 4 * d, T, 1, 0, "up dW"), (4 * d, d, T, 1, 0, "down dW")]:
+    """The twelve Linear GEMMs of one transformer block (forward NN, dX NT, dW TN), bf16 in / bf16 out.
+    `tp` in the shape: the per-rank shapes under tensor parallelism (column-parallel N / tp, row-parallel K / tp)."""
+    T, d, t = sh["T"], sh["d"], sh.get("tp", 1)
+    tot_us, tot_fl = 0.0, 0.0
+    for M, N, K, ta, tb, what in [(T, 3 * d // t, d, 0, 0, "qkv fwd"), (T, d, d // t, 0, 0, "out fwd"), (T, 4 * d // t, d, 0, 0, "up fwd"),
+                                  (T, d, 4 * d // t, 0, 0, "down fwd"), (T, d, 3 * d // t, 0, 1, "qkv dX"), (T, d // t, d, 0, 1, "out dX"),
+                                  (T, d, 4 * d // t, 0, 1, "up dX"), (T, 4 * d // t, d, 0, 1, "down dX"), (d, 3 * d // t, T, 1, 0, "qkv dW"),
+                                  (d // t, d, T, 1, 0, "out dW"), (d, 4 * d // t, T, 1, 0, "up dW"), (4 * d // t, d, T, 1, 0, "down dW")]:
         a = torch.randn((K, M) if ta else (M, K), device="cuda").to(BF16)
         b = torch.randn((N, K) if tb else (K, N), device="cuda").to(BF16)
         dw = what.endswith("dW")
@@ -166,6 +169,9 @@ def gemm(sh, name):
         kw = dict(C_out=c, ldc=N) if dw else dict(Cb_out=c, ldcb=N)
         s = timeit_graph(lambda: ops.gemm(a, b, M, N, K, lda=a.shape[1], ldb=b.shape[1], trans_a=bool(ta), trans_b=bool(tb), mode=1, **kw))
         emit(f"gemm {what} {M}x{N}x{K}", name, s, flops=2.0 * M * N * K, timing="20 launches in one CUDA graph, operands L2-warm")
+        tot_us += s * 1e6
+        tot_fl += 2.0 * M * N * K
+    emit("gemm: the 12 Linear GEMMs of a block", name, tot_us * 1e-6, flops=tot_fl)
 
 
 def main():

@@ -42,6 +42,10 @@ int npt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int npt_pinned_alloc(void** out, size_t bytes);
 int npt_pinned_free(void* p);
 int npt_memcpy_async(void* dst, const void* src, size_t bytes, int32_t kind, void* stream);
+/* device-to-device copy of `rows` rows of `width_bytes` bytes between pitched buffers (re-assembling the vocabulary
+ * shards of the tied embedding into one table: nn/embedding.py:19-37 shards it over the vocabulary axis) */
+int npt_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                       void* stream);
 
 /* ---- dense contractions ---------------------------------------------------------------
  * One strided-batched GEMM serves every contraction on the path:

@@ -102,6 +102,7 @@ static bool use_simt(const npt_gemm_args& a) {
 }
 
 static int choose_splits(const npt_gemm_args& a) {
+  if (a.C_bf16_peer) return 1;   // the peer store is part of the tile epilogue: no split-K (small-batch launches would pick it)
   if (use_simt(a)) return gemm_simt_splits(a);
   if (a.mode == NPT_GEMM_TF32X3_TC) return gemm_tf32_splits(a);
   return gemm_tc_splits(a);

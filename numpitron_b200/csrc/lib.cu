@@ -91,4 +91,12 @@ int npt_memcpy_async(void* dst, const void* src, size_t bytes, int32_t kind, voi
   return 0;
 }
 
+int npt_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                       void* stream) {
+  if (width_bytes == 0 || rows == 0) return 0;
+  NPT_REQUIRE(dst_pitch >= width_bytes && src_pitch >= width_bytes, "memcpy2d_async: pitch smaller than the row width");
+  NPT_CHECK_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
 }  // extern "C"

@@ -5,6 +5,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import distributed as npdist
+from ..distributed import peer
 from .. import ops
 from .. import runtime as rt
 from . import functional as F
@@ -30,6 +31,9 @@ class InputEmbedding(Layer):
             chunks[1:] += total_vocab_size % tp
             npdist.set_var("embedding_chunk_start", int(chunks[npdist.tensor_parallel_rank()]))
             npdist.set_var("embedding_chunk_end", int(chunks[npdist.tensor_parallel_rank() + 1]))
+            # every rank's bounds and shard width (np.array_split), for the small-vocabulary path of forward()
+            self._chunks = [int(c) for c in chunks[:tp + 1]]
+            self._widths = [total_vocab_size // tp + (1 if r < total_vocab_size % tp else 0) for r in range(tp)]
 
     def all_gather(self):
         super().all_gather()
@@ -41,6 +45,42 @@ class InputEmbedding(Layer):
             return npdist.get_var("embedding_chunk_start"), npdist.get_var("embedding_chunk_end")
         return 0, self.embedding.data.shape[1]  # un-scattered: the mask is computed but unused
 
+    def gathers_full_table(self, n_tokens: int) -> bool:
+        """Tensor parallelism with a vocabulary much smaller than the batch (the Shakespeare shape: 65 tokens,
+        32768 rows): instead of all-reducing the (B,S,d) fp32 result of the masked per-shard gathers
+        (embedding.py:61-62, 50 MB per step), the shards themselves are all-gathered (d x V floats) and every rank
+        gathers from the whole table.  Same bits: each token lies in exactly one rank's chunk, so the
+        reference's sum has one non-zero term.  Only when the reference's chunk bounds coincide with the shard
+        widths (they do whenever vocab % tp <= 1)."""
+        tp = npdist.tensor_parallel_size()
+        if not (self.is_scattered and tp > 1 and rt.has_gpu() and getattr(self, "_chunks", None)):
+            return False
+        consistent = all(self._chunks[r + 1] - self._chunks[r] == self._widths[r] for r in range(tp)) and \
+            self._chunks[tp] == sum(self._widths)
+        return consistent and 8 * sum(self._widths) <= n_tokens
+
+    def _full_table(self):
+        """(d, V) table re-assembled from the shards: own shard -> padded staging row block, one small NCCL
+        all-gather, tp pitched copies into place."""
+        import torch
+        import torch.distributed as dist
+
+        lib = __import__("numpitron_b200._lib", fromlist=["load"]).load()
+        tp, me = npdist.tensor_parallel_size(), npdist.tensor_parallel_rank()
+        E = self.embedding.data
+        d, wmax, V = E.shape[0], max(self._widths), sum(self._widths)
+        stage = rt.zeros((d, wmax)) if wmax != E.shape[1] else E
+        if stage is not E:
+            ops.check(lib.npt_memcpy2d_async(stage.data_ptr(), wmax * 4, E.data_ptr(), E.stride(0) * 4, E.shape[1] * 4, d, rt.stream()),
+                      "npt_memcpy2d_async")
+        gathered = rt.empty((tp, d, wmax))
+        dist.all_gather_into_tensor(gathered, stage, group=npdist.tensor_parallel_group().pg)
+        full = rt.empty((d, V))
+        for r in range(tp):
+            ops.check(lib.npt_memcpy2d_async(full.data_ptr() + self._chunks[r] * 4, V * 4, gathered[r].data_ptr(), wmax * 4,
+                                             self._widths[r] * 4, d, rt.stream()), "npt_memcpy2d_async")
+        return full
+
     def forward(self, inputs, pos=None):
         """inputs (B,S) uint16 tokens -> (B,S,d); out-of-chunk tokens give zero rows.
         `pos`: the positional-encoding table; when given (Transformer.forward at tp = 1, where no all-reduce
@@ -48,6 +88,13 @@ class InputEmbedding(Layer):
         done by the same kernel, with the same single fp32 addition."""
         lo, hi = self._bounds()
         seq_len = inputs.shape[-1]
+        if self.gathers_full_table(inputs.numel()):
+            full = self._full_table()
+            outputs = ops.embedding_gather(inputs, full, pos, seq_len, 0, full.shape[1], False,
+                                           want_bf16=pos is not None and rt.is_bf16())
+            self.ctx["inputs"] = inputs
+            self.ctx["bounds"] = (lo, hi)
+            return outputs
         outputs = ops.embedding_gather(inputs, self.embedding.data, pos, seq_len, lo, hi, self.is_scattered,
                                        want_bf16=pos is not None and rt.is_bf16())
         if self.is_scattered and npdist.tensor_parallel_size() > 1:
@@ -84,8 +131,20 @@ class OutputEmbedding(Layer):
         # (the value it would otherwise be cast to): let the GEMM epilogue write bf16 directly.
         d_model = self.input_embedding.embedding.data.shape[0]
         out = "bf16" if rt.is_bf16() and ops.layernorm_bf16_input_supported(d_model) else "f32"
+        tp = self.is_scattered and npdist.tensor_parallel_size() > 1
+        if tp and out == "bf16" and peer.enabled():
+            # tp = 2: no all-reduce kernel — the partial goes to the other rank's memory from the GEMM epilogue and
+            # the last block's LayerNorm backward adds the two partials while it reads (distributed/peer.py)
+            shape = (*d_out.shape[:-1], d_model)
+            px = peer.exchange(shape)
+            if px is not None:
+                slot, send_ptr, recv_ptr = px.slot("bwd", shape)
+                d_in = F.linear_backward_input(d_out, self.input_embedding, "embedding", out="bf16", out_tensor=slot,
+                                               peer_out=send_ptr)
+                d_in._npt_peer = (px, recv_ptr)
+                return d_in
         d_out = F.linear_backward_input(d_out, self.input_embedding, "embedding", out=out)
-        if self.is_scattered and npdist.tensor_parallel_size() > 1:
+        if tp:
             npdist.all_reduce(d_out, group=npdist.tensor_parallel_group())
         return d_out
 

@@ -39,7 +39,7 @@ class Transformer(Model):
     def forward(self, inputs):
         """Model.forward (nn/model.py:15-18).  Without tensor parallelism nothing sits between the embedding
         gather and the positional add, so both run in one kernel (same arithmetic, one pass less)."""
-        if npdist.tensor_parallel_size() > 1:
+        if npdist.tensor_parallel_size() > 1 and not self.input_embedding.gathers_full_table(inputs.numel()):
             return super().forward(inputs)
         layers = list(self.layers.values())
         outputs = self.input_embedding.forward(inputs, pos=self.positional_encoding.encoding)

@@ -61,7 +61,9 @@ def main(tp, dp, precision):
     w_got = to_numpy(model.block_0.mlp.column_linear.weight.data)
     w_want = W[f"rank{rank}/w1_final_block0"]
     if precision == "fp32":
-        close(w_got, w_want, rtol, "w1_final")
+        # 3xTF32 contractions differ from the reference's by ~1e-6 relative in a gradient; through Adam's
+        # m / (sqrt(v) + eps) that is a fraction of a percent of one lr step on single weights (measured 2.6e-7)
+        assert np.abs(w_got - w_want).max() <= 1e-6, np.abs(w_got - w_want).max()
     else:
         diff = np.abs(w_got - w_want)
         assert diff.max() <= 6.1e-4 and diff.mean() <= 5e-5, (diff.max(), diff.mean())
