@@ -93,6 +93,11 @@ typedef struct npt_gemm_args {
    * nn/mlp.py:34) lands next to the peer's own partial while the GEMM is still running, and the LayerNorm
    * that follows adds the two from local memory (npt_layernorm_fwd_v2, x_peer). */
   void* C_bf16_peer;
+  /* peer_rows_hi > peer_rows_lo: SPLIT store instead of a double store — tiles whose rows lie in
+   * [peer_rows_lo, peer_rows_hi) go to C_bf16_peer ONLY, all others to C_bf16 only (both bounds multiples of 128).
+   * That is a reduce-scatter by push: each rank ends up with both partials of the rows it owns and normalises
+   * only those (npt_layernorm_fwd_v3 / _bwd_v4), instead of every rank reducing and normalising all rows. */
+  int32_t peer_rows_lo, peer_rows_hi;
   /* 1: when the launch is split along K (npt_gemm_splits() > 1) leave the fp32 partials
    * [split][batch][M][N] in `workspace` and do NOT reduce them into C — the consumer adds them in split
    * order (npt_adam_tensor.g_splits: the weight gradients of nn/linear.py:55 are only ever read by Adam,
@@ -162,6 +167,28 @@ int npt_layernorm_bwd_v3(const void* x, const void* dy, int32_t inputs_are_bf16,
                          void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int64_t rows,
                          int32_t d, float eps, void* workspace, size_t workspace_bytes,
                          int32_t defer_reduce, int32_t* n_partials, void* stream);
+
+/* Row-sharded LayerNorm under tensor parallelism over 2 ranks (tp = 2, bf16 mode).  The GEMM in front stored its
+ * partial split by rows (npt_gemm_args.peer_rows_*), so this rank holds BOTH partials of the rows it owns: it
+ * normalises only those (the pointers passed are those of its first row, `rows` = its row count) and pushes its half
+ * of every tensor the next kernels need in full into the other rank's memory — forward: y_bf16_peer; backward:
+ * dx_bf16_peer and the per-block dgamma / dbeta / colsum partials (workspace_peer; each rank's stack of
+ * npt_layernorm_bwd_partials() blocks sits behind the other's in one [2][n][2 or 3][d] buffer that both hold
+ * after the caller's barrier).  fwd_v3 / bwd_v4 = fwd_v2 / bwd_v3 plus those destinations (NULL = none). */
+int npt_layernorm_fwd_v3(const void* x, int32_t x_is_bf16, const void* x_peer, void* x_sum_bf16,
+                         const float* gamma, const float* beta, const float* residual, float* y,
+                         void* y_bf16, void* y_bf16_peer, float* mean, float* var, int64_t rows, int32_t d,
+                         float eps, void* stream);
+int npt_layernorm_bwd_v4(const void* x, const void* dy, int32_t inputs_are_bf16, const void* dy_peer,
+                         const float* gamma, const float* mean, const float* var, float* dx,
+                         void* dx_bf16, void* dx_bf16_peer, float* dgamma, float* dbeta, float* dx_colsum,
+                         int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
+                         void* workspace_peer, int32_t defer_reduce, int32_t* n_partials, void* stream);
+/* number of per-block partials the first stage of npt_layernorm_bwd_* leaves for these arguments */
+int32_t npt_layernorm_bwd_partials(int64_t rows, int32_t d, int32_t inputs_are_bf16);
+/* second stage alone: dgamma / dbeta (/ dx_colsum, n_slices = 3) = block-order sums of partials[n_partials][n_slices][d] */
+int npt_layernorm_bwd_reduce(const float* partials, int32_t n_partials, int32_t n_slices, int32_t d,
+                             float* dgamma, float* dbeta, float* dx_colsum, void* stream);
 
 /* ---- ReLU — nn/activation.py:38-43 (stand-alone; the GEMM epilogue fuses both) ---------- */
 int npt_relu_fwd(const float* x, float* y, void* y_bf16, int64_t n, void* stream);

@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("relu_bits_out", c_void_p), ("mask_bits", c_void_p), ("ld_bits", c_int64),
         ("C_bf16_peer", c_void_p),
+        ("peer_rows_lo", c_int32), ("peer_rows_hi", c_int32),
         ("skip_splitk_reduce", c_int32),
     ]
 
@@ -74,6 +75,11 @@ _SIGNATURES = {
     "npt_layernorm_bf16_input_supported": (c_int, [c_int32]),
     "npt_layernorm_fwd_v2": (c_int, [_P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P]),
     "npt_layernorm_bwd_v2": (c_int, [_P, _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P, c_size_t, _P]),
+    "npt_layernorm_fwd_v3": (c_int, [_P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P]),
+    "npt_layernorm_bwd_v4": (c_int, [_P, _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P, c_size_t,
+                                     _P, c_int32, _P, _P]),
+    "npt_layernorm_bwd_partials": (c_int32, [c_int64, c_int32, c_int32]),
+    "npt_layernorm_bwd_reduce": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "npt_layernorm_bwd_v3": (c_int, [_P, _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, _P, c_size_t,
                                      c_int32, _P, _P]),
     "npt_relu_fwd": (c_int, [_P, _P, _P, c_int64, _P]),

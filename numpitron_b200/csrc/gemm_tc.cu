@@ -208,6 +208,7 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
   p.total_tiles = (int)total;
   p.raw = splits > 1;
   p.peer_store = 0;
+  p.peer_lo = p.peer_hi = 0;
 #ifdef NPT_GEMM_DEBUG
   {
     const char* d = getenv("NUMPITRON_GEMM_DBG");
@@ -264,6 +265,13 @@ int gemm_tc_launch(const npt_gemm_args& a, const GemmEpilogue& epi, int splits, 
                   a.stride_cb_inner, n_bo, a.stride_cb_outer, 64, 32);
     if (rc) return rc;
     p.peer_store = 1;
+    if (a.peer_rows_hi > a.peer_rows_lo) {
+      NPT_REQUIRE(a.peer_rows_lo % TC_BM == 0 && a.peer_rows_hi % TC_BM == 0 && a.batch == 1,
+                  "gemm(tc): peer_rows bounds must be multiples of %d (got %d, %d) and the launch unbatched", TC_BM, a.peer_rows_lo, a.peer_rows_hi);
+      p.peer_store = 2;
+      p.peer_lo = a.peer_rows_lo;
+      p.peer_hi = a.peer_rows_hi;
+    }
   }
   NPT_REQUIRE(cl == 1 || kind != EPI_GENERAL, "gemm(tc): internal error, CTA pairs need the fast epilogue");
   const bool a_mn = a.trans_a != 0, b_mn = a.trans_b == 0;

@@ -242,7 +242,8 @@ struct TcParams {
   int m_tiles, n_tiles, total_tiles;
   int tma_store;  // 1: staged TMA-store epilogue; 0: direct register stores (unaligned outputs)
   int raw;        // 1: split-K partial (no epilogue math), stored through map C as {N, M, batch, split}
-  int peer_store; // 1: the bf16 output is also stored through map P (a peer GPU's buffer)
+  int peer_store; // 1: the bf16 output is also stored through map P (a peer GPU's buffer); 2: rows in [peer_lo, peer_hi) go to P only
+  int peer_lo, peer_hi;
 #ifdef NPT_GEMM_DEBUG
   int dbg;        // timing experiments only: 1 = no epilogue stores, 2 = no MMA issue, 4 = no TMA loads
   long long* trace;  // [cta][64] clock64() stamps (slot 0/1: entry / after prologue, then 7 per tile)
@@ -586,9 +587,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(out_map, stage_base + (store_i & 1) * L::FAST_SLOT_BYTES, out_bf16 ? nb - 32 : nb, mrow0, c2, c3);
-            // tensor parallelism: the same staged tile also goes to the peer GPU (posted NVLink writes)
-            if (p.peer_store) tma_store_4d(&tmP, stage_base + (store_i & 1) * L::FAST_SLOT_BYTES, nb - 32, mrow0, c2, c3);
+            // tensor parallelism: the staged tile also (peer_store 1) or instead (2: rows the peer owns) goes to
+            // the peer GPU (posted NVLink writes)
+            const bool peer_only = p.peer_store == 2 && mrow0 >= p.peer_lo && mrow0 < p.peer_hi;
+            if (!peer_only) tma_store_4d(out_map, stage_base + (store_i & 1) * L::FAST_SLOT_BYTES, out_bf16 ? nb - 32 : nb, mrow0, c2, c3);
+            if (p.peer_store == 1 || peer_only) tma_store_4d(&tmP, stage_base + (store_i & 1) * L::FAST_SLOT_BYTES, nb - 32, mrow0, c2, c3);
             tma_store_commit();
           }
           ++store_i;

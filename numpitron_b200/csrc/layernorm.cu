@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 ln_fwd_warp_kernel(const void* __restrict__ x, const void* __restrict__ x_peer, __nv_bfloat16* __restrict__ x_sum,
                    const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ residual,
-                   float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
+                   float* __restrict__ y, __nv_bfloat16* __restrict__ yb, __nv_bfloat16* __restrict__ yb_peer,
                    float* __restrict__ mean_out, float* __restrict__ var_out,
                    int64_t rows, int d, float eps) {
   pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
@@ -127,6 +127,7 @@ ln_fwd_warp_kernel(const void* __restrict__ x, const void* __restrict__ x_peer, 
       }
       st_stream(yr + c, o);
       if (yb) st_bf16x4(yb + row * d + (int64_t)c * 4, o);
+      if (PEER && yb_peer) st_bf16x4(yb_peer + row * d + (int64_t)c * 4, o);   // all-gather by push (row-sharded LayerNorm)
     }
   }
 }
@@ -176,8 +177,8 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 ln_bwd_warp_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ mean_in, const float* __restrict__ var_in,
                    const void* __restrict__ dy, const void* __restrict__ dy_peer, float* __restrict__ dx,
-                   __nv_bfloat16* __restrict__ dxb, float* __restrict__ partial,
-                   int64_t rows, int d, float eps) {
+                   __nv_bfloat16* __restrict__ dxb, __nv_bfloat16* __restrict__ dxb_peer, float* __restrict__ partial,
+                   float* __restrict__ partial_peer, int64_t rows, int d, float eps) {
   pdl_wait();  // programmatic dependent launch: predecessors complete, then let the successor set up
   pdl_trigger();
   extern __shared__ float sm[];  // [kLnWarps][NSL][d]
@@ -272,6 +273,7 @@ ln_bwd_warp_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
           }
           if (dx) st_stream(outr + c, o);
           if (dxb) st_bf16x4(dxb + row * d + (int64_t)c * 4, o);
+          if (PEER && dxb_peer) st_bf16x4(dxb_peer + row * d + (int64_t)c * 4, o);   // all-gather by push
           if (DXSUM) {
             float4 t = dsum[c];
             t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
@@ -297,6 +299,7 @@ ln_bwd_warp_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
 #pragma unroll
     for (int w2 = 0; w2 < kLnWarps; ++w2) t += sm[(size_t)w2 * NSL * d + c];
     partial[(size_t)blockIdx.x * NSL * d + c] = t;
+    if (PEER && partial_peer) partial_peer[(size_t)blockIdx.x * NSL * d + c] = t;
   }
 }
 
@@ -326,8 +329,8 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 ln_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean_in, const float* __restrict__ var_in,
                      const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy_peer,
-                     float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, float* __restrict__ partial,
-                     int64_t rows, int d, float eps, int R) {
+                     float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, __nv_bfloat16* __restrict__ dxb_peer,
+                     float* __restrict__ partial, float* __restrict__ partial_peer, int64_t rows, int d, float eps, int R) {
   constexpr int NT = PEER ? 3 : 2;       // row tensors per slot: x, dy (, the other rank's dy)
   constexpr int NSL = DXSUM ? 3 : 2;
   extern __shared__ __align__(16) uint8_t ln_smem[];
@@ -427,6 +430,7 @@ ln_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
         o.w = (w[i].w - c1 * xh[i].w - c2) * rstd;
         if (dx) st_stream(reinterpret_cast<float4*>(dx + row * d) + c, o);
         if (dxb) st_bf16x4(dxb + row * d + (int64_t)c * 4, o);
+        if (PEER && dxb_peer) st_bf16x4(dxb_peer + row * d + (int64_t)c * 4, o);   // all-gather by push
         if (DXSUM) {
           float4 t = dsum[c];
           t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
@@ -458,7 +462,10 @@ ln_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
     }
     __syncthreads();
   }
-  for (int c = threadIdx.x; c < NSL * d; c += blockDim.x) partial[(size_t)blockIdx.x * NSL * d + c] = comb[c];
+  for (int c = threadIdx.x; c < NSL * d; c += blockDim.x) {
+    partial[(size_t)blockIdx.x * NSL * d + c] = comb[c];
+    if (PEER && partial_peer) partial_peer[(size_t)blockIdx.x * NSL * d + c] = comb[c];
+  }
 }
 
 // Any d: block per row-group, scalar loops.  partial layout identical.
@@ -540,37 +547,43 @@ static int ln_bwd_blocks(int64_t rows) {
 
 template <int NV>
 static int launch_fwd(const void* x, bool in_bf16, const void* xp, void* xs, const float* g, const float* b, const float* r, float* y,
-                      void* yb, float* mean, float* var, int64_t rows, int d, float eps,
+                      void* yb, void* ybp, float* mean, float* var, int64_t rows, int d, float eps,
                       cudaStream_t st) {
   const int64_t grid = cdiv(rows, kLnWarps);
   if (in_bf16 && xp)
     NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, 3>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
-        x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
+        x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, (__nv_bfloat16*)ybp, mean, var, rows, d, eps));
   else if (in_bf16)
     NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, 2>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
-        x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
+        x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, (__nv_bfloat16*)ybp, mean, var, rows, d, eps));
   else if (yb)  // bf16 throughput mode
     NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, 1>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
-        x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
+        x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, (__nv_bfloat16*)ybp, mean, var, rows, d, eps));
   else
     NPT_CHECK_CUDA(launch_pdl(ln_fwd_warp_kernel<NV, 0>, dim3((unsigned)grid), dim3(kLnWarps * 32), 0, st,
-        x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, mean, var, rows, d, eps));
+        x, xp, (__nv_bfloat16*)xs, g, b, r, y, (__nv_bfloat16*)yb, (__nv_bfloat16*)ybp, mean, var, rows, d, eps));
   NPT_LAUNCH_CHECK();
   return 0;
 }
 
+struct LnPeerOut { void* dxb_peer; float* partial_peer; };   // row-sharded mode: second (peer-GPU) destinations
+
 template <int NV, int MODE, bool DXSUM>
 static int launch_bwd_k(const void* x, const float* g, const float* mean, const float* var, const void* dy, const void* dyp, float* dx,
-                        void* dxb, float* partial, int nblocks, int64_t rows, int d, float eps, cudaStream_t st) {
+                        void* dxb, float* partial, int nblocks, int64_t rows, int d, float eps, const LnPeerOut& po, cudaStream_t st) {
   const size_t smem = (size_t)kLnWarps * (DXSUM ? 3 : 2) * d * sizeof(float);
   auto kern = ln_bwd_warp_kernel<NV, MODE, DXSUM>;
   NPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NPT_CHECK_CUDA(launch_pdl(kern, dim3(nblocks), dim3(kLnWarps * 32), smem, st, x, g, mean, var, dy, dyp, dx,
-                            (__nv_bfloat16*)dxb, partial, rows, d, eps));
+                            (__nv_bfloat16*)dxb, (__nv_bfloat16*)po.dxb_peer, partial, po.partial_peer, rows, d, eps));
   NPT_LAUNCH_CHECK();
   return 0;
 }
 
+static int ln_stream_blocks(int64_t rows) {
+  const int64_t want = cdiv(rows, kLnWarps), cap = (int64_t)sm_count() * 2;
+  return (int)(want < cap ? want : cap);
+}
 static size_t ln_stream_smem(int d, int R, bool peer, bool dxsum) {
   return (size_t)kLnWarps * R * (peer ? 3 : 2) * d * 2 + (dxsum ? (size_t)kLnWarps * d * 4 : 0) + (size_t)(dxsum ? 3 : 2) * d * 4 +
          (size_t)kLnWarps * R * 8;
@@ -584,43 +597,35 @@ static int ln_stream_slots(int d, bool peer) {
 
 template <int NV, bool PEER, bool DXSUM>
 static int launch_bwd_stream_k(const void* x, const float* g, const float* mean, const float* var, const void* dy, const void* dyp,
-                               float* dx, void* dxb, float* partial, int* nblocks, int64_t rows, int d, float eps, cudaStream_t st) {
+                               float* dx, void* dxb, float* partial, int* nblocks, int64_t rows, int d, float eps, const LnPeerOut& po, cudaStream_t st) {
   const int R = ln_stream_slots(d, PEER);
   const size_t smem = ln_stream_smem(d, R, PEER, DXSUM);
   auto kern = ln_bwd_stream_kernel<NV, PEER, DXSUM>;
-  static int per_sm = 0;
-  static size_t per_sm_smem = 0;
-  if (per_sm == 0 || per_sm_smem != smem) {
-    NPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NPT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLnWarps * 32, smem));
-    if (per_sm < 1) per_sm = 1;
-    per_sm_smem = smem;
-  }
-  int64_t want = cdiv(rows, kLnWarps);
-  const int64_t cap = (int64_t)sm_count() * (per_sm > 2 ? 2 : per_sm);   // the partial workspace holds 2 blocks per SM
-  *nblocks = (int)(want < cap ? want : cap);
+  NPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  *nblocks = ln_stream_blocks(rows);   // the partial workspace holds 2 blocks per SM
   NPT_CHECK_CUDA(launch_pdl(kern, dim3(*nblocks), dim3(kLnWarps * 32), smem, st, (const __nv_bfloat16*)x, g, mean, var,
-                            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dyp, dx, (__nv_bfloat16*)dxb, partial, rows, d, eps, R));
+                            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dyp, dx, (__nv_bfloat16*)dxb, (__nv_bfloat16*)po.dxb_peer, partial,
+                            po.partial_peer, rows, d, eps, R));
   NPT_LAUNCH_CHECK();
   return 0;
 }
 
 template <int NV>
 static int launch_bwd_stream(const void* x, const float* g, const float* mean, const float* var, const void* dy, const void* dyp,
-                             float* dx, void* dxb, float* partial, bool dxsum, int* nblocks, int64_t rows, int d, float eps, cudaStream_t st) {
-  if (dyp) return dxsum ? launch_bwd_stream_k<NV, true, true>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st)
-                        : launch_bwd_stream_k<NV, true, false>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st);
-  return dxsum ? launch_bwd_stream_k<NV, false, true>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st)
-               : launch_bwd_stream_k<NV, false, false>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st);
+                             float* dx, void* dxb, float* partial, bool dxsum, int* nblocks, int64_t rows, int d, float eps, const LnPeerOut& po, cudaStream_t st) {
+  if (dyp) return dxsum ? launch_bwd_stream_k<NV, true, true>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, po, st)
+                        : launch_bwd_stream_k<NV, true, false>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, po, st);
+  return dxsum ? launch_bwd_stream_k<NV, false, true>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, po, st)
+               : launch_bwd_stream_k<NV, false, false>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, po, st);
 }
 
 template <int NV>
 static int launch_bwd(const void* x, const float* g, const float* mean, const float* var,
                       const void* dy, const void* dyp, bool in_bf16, float* dx, void* dxb, float* partial, bool dxsum, int nblocks,
-                      int64_t rows, int d, float eps, cudaStream_t st) {
+                      int64_t rows, int d, float eps, const LnPeerOut& po, cudaStream_t st) {
 #define NPT_LN_BWD(MODE)                                                                                        \
-  return dxsum ? launch_bwd_k<NV, MODE, true>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st) \
-               : launch_bwd_k<NV, MODE, false>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, st)
+  return dxsum ? launch_bwd_k<NV, MODE, true>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, po, st) \
+               : launch_bwd_k<NV, MODE, false>(x, g, mean, var, dy, dyp, dx, dxb, partial, nblocks, rows, d, eps, po, st)
   if (in_bf16 && dyp) { NPT_LN_BWD(3); }
   if (in_bf16) { NPT_LN_BWD(2); }
   if (dxb) { NPT_LN_BWD(1); }  // bf16 throughput mode
@@ -646,6 +651,14 @@ int npt_layernorm_fwd_v2(const void* x, int32_t x_is_bf16, const void* x_peer, v
                          const float* beta, const float* residual,
                          float* y, void* y_bf16, float* mean, float* var, int64_t rows, int32_t d,
                          float eps, void* stream) {
+  return npt_layernorm_fwd_v3(x, x_is_bf16, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, nullptr, mean, var, rows, d, eps, stream);
+}
+
+int npt_layernorm_fwd_v3(const void* x, int32_t x_is_bf16, const void* x_peer, void* x_sum_bf16, const float* gamma,
+                         const float* beta, const float* residual,
+                         float* y, void* y_bf16, void* y_bf16_peer, float* mean, float* var, int64_t rows, int32_t d,
+                         float eps, void* stream) {
+  NPT_REQUIRE(!y_bf16_peer || (x_peer && y_bf16 && aligned8(y_bf16_peer)), "layernorm_fwd: y_bf16_peer needs x_peer and y_bf16");
   NPT_REQUIRE(rows >= 0 && d > 0, "layernorm_fwd: bad shape rows=%lld d=%d", (long long)rows, d);
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -659,12 +672,12 @@ int npt_layernorm_fwd_v2(const void* x, int32_t x_is_bf16, const void* x_peer, v
     const int nv = (int)cdiv(d, 128);
     const bool ib = x_is_bf16 != 0;
     switch (nv) {
-      case 1: return launch_fwd<1>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      case 2: return launch_fwd<2>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      case 3: return launch_fwd<3>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      case 4: return launch_fwd<4>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      case 5: case 6: return launch_fwd<6>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
-      default: return launch_fwd<8>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, mean, var, rows, d, eps, st);
+      case 1: return launch_fwd<1>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, y_bf16_peer, mean, var, rows, d, eps, st);
+      case 2: return launch_fwd<2>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, y_bf16_peer, mean, var, rows, d, eps, st);
+      case 3: return launch_fwd<3>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, y_bf16_peer, mean, var, rows, d, eps, st);
+      case 4: return launch_fwd<4>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, y_bf16_peer, mean, var, rows, d, eps, st);
+      case 5: case 6: return launch_fwd<6>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, y_bf16_peer, mean, var, rows, d, eps, st);
+      default: return launch_fwd<8>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, y_bf16_peer, mean, var, rows, d, eps, st);
     }
   }
   NPT_CHECK_CUDA(launch_pdl(ln_fwd_block_kernel, dim3((unsigned)rows), dim3(256), 0, st, (const float*)x, gamma, beta, residual, y,
@@ -701,15 +714,49 @@ int npt_layernorm_bwd_v3(const void* x, const void* dy, int32_t inputs_are_bf16,
                          const float* var, float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum,
                          int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes,
                          int32_t defer_reduce, int32_t* n_partials, void* stream) {
+  return npt_layernorm_bwd_v4(x, dy, inputs_are_bf16, dy_peer, gamma, mean, var, dx, dx_bf16, nullptr, dgamma, dbeta, dx_colsum, rows, d,
+                              eps, workspace, workspace_bytes, nullptr, defer_reduce, n_partials, stream);
+}
+
+// Which first-stage kernel runs, and with how many blocks (= per-block partials left in the workspace).
+static bool ln_bwd_streams(int32_t d, bool ib) {
+  return (d % 4 == 0) && d <= kLnMaxVec * 128 && ib && d > 512 && d % 8 == 0 && !ln_bwd_force_register();
+}
+int32_t npt_layernorm_bwd_partials(int64_t rows, int32_t d, int32_t inputs_are_bf16) {
+  if (rows <= 0 || d <= 0) return 0;
+  if (ln_bwd_streams(d, inputs_are_bf16 != 0)) return ln_stream_blocks(rows);
+  if (d % 4 == 0 && d <= kLnMaxVec * 128) return ln_bwd_blocks(rows);
+  const int64_t cap = (int64_t)sm_count() * 2;
+  return (int32_t)(rows < cap ? rows : cap);
+}
+
+int npt_layernorm_bwd_reduce(const float* partials, int32_t n_partials, int32_t n_slices, int32_t d, float* dgamma, float* dbeta,
+                             float* dx_colsum, void* stream) {
+  NPT_REQUIRE(partials && n_partials > 0 && (n_slices == 2 || n_slices == 3) && d > 0 && dgamma && dbeta && (n_slices == 2 || dx_colsum),
+              "layernorm_bwd_reduce: bad arguments");
+  NPT_CHECK_CUDA(launch_pdl(reduce_partials_kernel, dim3((unsigned)cdiv(n_slices * (int64_t)d, 128)), dim3(128), 0, (cudaStream_t)stream,
+                            partials, dgamma, dbeta, dx_colsum, (int)n_slices, (int)n_partials, (int)d));
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int npt_layernorm_bwd_v4(const void* x, const void* dy, int32_t inputs_are_bf16, const void* dy_peer, const float* gamma, const float* mean,
+                         const float* var, float* dx, void* dx_bf16, void* dx_bf16_peer, float* dgamma, float* dbeta, float* dx_colsum,
+                         int64_t rows, int32_t d, float eps, void* workspace, size_t workspace_bytes, void* workspace_peer,
+                         int32_t defer_reduce, int32_t* n_partials, void* stream) {
   NPT_REQUIRE(rows > 0 && d > 0, "layernorm_bwd: bad shape rows=%lld d=%d", (long long)rows, d);
+  NPT_REQUIRE((!dx_bf16_peer && !workspace_peer) || (dy_peer && dx_bf16 && defer_reduce),
+              "layernorm_bwd: peer outputs need dy_peer, dx_bf16 and defer_reduce (the caller reduces both ranks' partials)");
+  const LnPeerOut po{dx_bf16_peer, (float*)workspace_peer};
   NPT_REQUIRE(dx || dx_bf16, "layernorm_bwd: no output");
-  NPT_REQUIRE(workspace && workspace_bytes >= npt_layernorm_bwd_workspace_bytes(rows, d),
-              "layernorm_bwd: workspace too small (%zu < %zu)", workspace_bytes,
-              npt_layernorm_bwd_workspace_bytes(rows, d));
+  const bool ib = inputs_are_bf16 != 0;
+  {
+    const size_t need = (size_t)npt_layernorm_bwd_partials(rows, d, inputs_are_bf16) * (dx_colsum ? 3 : 2) * (size_t)d * sizeof(float);
+    NPT_REQUIRE(workspace && workspace_bytes >= need, "layernorm_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+  }
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = (float*)workspace;
   int nblocks;
-  const bool ib = inputs_are_bf16 != 0;
   const bool vec = (d % 4 == 0) && d <= kLnMaxVec * 128 && (ib ? aligned8(x) && aligned8(dy) : aligned16(x) && aligned16(dy)) &&
                    (!dx || aligned16(dx)) && aligned16(gamma) && (!dx_bf16 || aligned8(dx_bf16)) &&
                    (size_t)kLnWarps * 3 * d * sizeof(float) <= 200 * 1024;
@@ -719,17 +766,17 @@ int npt_layernorm_bwd_v3(const void* x, const void* dy, int32_t inputs_are_bf16,
               "layernorm_bwd: fused dx column sums / bf16 inputs need d %% 4 == 0, d <= %d and aligned buffers", kLnMaxVec * 128);
   // measured (benchmarks/kernbench.py): rows of <= 512 columns fit the register kernel's two-rows-in-flight scheme
   // (18 us vs 22 us at 16384 x 384); wider rows run 1.6-2x faster on the streaming kernel (32768 x 768: 76 us vs 145 us)
-  const bool stream_ok = vec && ib && d > 512 && d % 8 == 0 && aligned16(x) && aligned16(dy) && (!dy_peer || aligned16(dy_peer)) && !ln_bwd_force_register();
+  const bool stream_ok = vec && ln_bwd_streams(d, ib) && aligned16(x) && aligned16(dy) && (!dy_peer || aligned16(dy_peer));
   if (stream_ok) {
     const int nv = (int)cdiv(d, 128);
     int rc;
     switch (nv) {
-      case 1: rc = launch_bwd_stream<1>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, st); break;
-      case 2: rc = launch_bwd_stream<2>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, st); break;
-      case 3: rc = launch_bwd_stream<3>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, st); break;
-      case 4: rc = launch_bwd_stream<4>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, st); break;
-      case 5: case 6: rc = launch_bwd_stream<6>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, st); break;
-      default: rc = launch_bwd_stream<8>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, st); break;
+      case 1: rc = launch_bwd_stream<1>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, po, st); break;
+      case 2: rc = launch_bwd_stream<2>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, po, st); break;
+      case 3: rc = launch_bwd_stream<3>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, po, st); break;
+      case 4: rc = launch_bwd_stream<4>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, po, st); break;
+      case 5: case 6: rc = launch_bwd_stream<6>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, po, st); break;
+      default: rc = launch_bwd_stream<8>(x, gamma, mean, var, dy, dy_peer, dx, dx_bf16, partial, dxsum, &nblocks, rows, d, eps, po, st); break;
     }
     if (rc) return rc;
   } else if (vec) {
@@ -737,12 +784,12 @@ int npt_layernorm_bwd_v3(const void* x, const void* dy, int32_t inputs_are_bf16,
     const int nv = (int)cdiv(d, 128);
     int rc;
     switch (nv) {
-      case 1: rc = launch_bwd<1>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      case 2: rc = launch_bwd<2>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      case 3: rc = launch_bwd<3>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      case 4: rc = launch_bwd<4>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      case 5: case 6: rc = launch_bwd<6>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
-      default: rc = launch_bwd<8>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, st); break;
+      case 1: rc = launch_bwd<1>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, po, st); break;
+      case 2: rc = launch_bwd<2>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, po, st); break;
+      case 3: rc = launch_bwd<3>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, po, st); break;
+      case 4: rc = launch_bwd<4>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, po, st); break;
+      case 5: case 6: rc = launch_bwd<6>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, po, st); break;
+      default: rc = launch_bwd<8>(x, gamma, mean, var, dy, dy_peer, ib, dx, dx_bf16, partial, dxsum, nblocks, rows, d, eps, po, st); break;
     }
     if (rc) return rc;
   } else {

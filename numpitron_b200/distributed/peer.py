@@ -18,7 +18,18 @@ receive slot s for exchange i; B reads it after barrier i and A writes it again 
 after barrier i+1, which B only reaches once that read (earlier in B's stream) is done — so one
 barrier per exchange suffices.
 
-NUMPITRON_TP_PEER=0 disables this and keeps the NCCL all-reduces.
+Row-sharded LayerNorm (NUMPITRON_TP_ROWSPLIT=0 turns it off).  Reducing on both ranks means both ranks also
+normalise every row: LayerNorm, which is memory-bound, costs twice what it costs on one GPU.  When the rows
+split into two multiples of 128, the GEMM stores each tile ONCE — tiles of the rows this rank owns locally, the
+others into the peer's receive slot (`npt_gemm_args.peer_rows_*`: a reduce-scatter by push) — LayerNorm forward /
+backward run on the own half of the rows only and write the bf16 tensor the next GEMMs read (y, or dx) into a
+peer-visible ARENA buffer and into the peer's copy of it (an all-gather by push), followed by a second barrier.
+Same NVLink bytes as before, half the LayerNorm work and half the epilogue stores.  The per-block partials of
+dgamma / dbeta / bias gradient are pushed the same way; both ranks add the two stacks in the same order, so the
+replicated parameters stay bit-identical.  The arena is a bump allocator that `step_begin()` rewinds at the
+start of every forward pass: the same sequence of requests gets the same addresses every step (CUDA graphs).
+
+NUMPITRON_TP_PEER=0 disables all of this and keeps the NCCL all-reduces.
 """
 from __future__ import annotations
 
@@ -29,15 +40,17 @@ import torch
 
 from .. import runtime as rt
 
-_state = {"px": None, "failed": False}
+_state = {"px": None, "failed": False, "arena_bytes": 0}
 
 
 class PeerExchange:
-    def __init__(self, pg, slot_bytes: int):
+    def __init__(self, pg, slot_bytes: int, arena_bytes: int = 0):
         import torch.distributed._symmetric_memory as symm
 
         self.slot_bytes = (slot_bytes + 255) // 256 * 256
-        self.buf = symm.empty(8 * self.slot_bytes, dtype=torch.uint8, device=rt.device())
+        self.arena_bytes = (arena_bytes + 255) // 256 * 256
+        self.arena_base, self.arena_pos = 8 * self.slot_bytes, 0
+        self.buf = symm.empty(8 * self.slot_bytes + self.arena_bytes, dtype=torch.uint8, device=rt.device())
         self.hdl = symm.rendezvous(self.buf, pg)
         assert self.hdl.world_size == 2
         self.rank = self.hdl.rank
@@ -58,6 +71,33 @@ class PeerExchange:
         own_off, recv_off = i * self.slot_bytes, (i + 2) * self.slot_bytes
         own = self.buf[own_off:own_off + nbytes].view(dtype).view(*shape)
         return own, self.peer_base + recv_off, self.buf.data_ptr() + recv_off
+
+    # -- row-sharded LayerNorm ------------------------------------------------------------------------
+    def step_begin(self):
+        self.arena_pos = 0
+
+    def rows(self, n_rows: int):
+        """(first row, row count) this rank owns, or None when the rows do not split into two multiples of 128
+        (the GEMM routes whole 128-row tiles) or no arena was configured."""
+        half = n_rows // 2
+        if self.arena_bytes == 0 or n_rows % 2 or half % 128 or os.environ.get("NUMPITRON_TP_ROWSPLIT", "1") == "0":
+            return None
+        return self.rank * half, half
+
+    def peer_rows(self, n_rows: int):
+        half = n_rows // 2
+        return (1 - self.rank) * half, (2 - self.rank) * half
+
+    def arena(self, shape, dtype):
+        """Next peer-visible buffer of the step: (local tensor, address of the same buffer in the peer's memory)."""
+        n = 1
+        for k in shape:
+            n *= int(k)
+        nbytes = (n * torch.empty((), dtype=dtype).element_size() + 255) // 256 * 256
+        assert self.arena_pos + nbytes <= self.arena_bytes, "peer arena too small (peer.prepare sizes it from the model)"
+        off = self.arena_base + self.arena_pos
+        self.arena_pos += nbytes
+        return self.buf[off:off + nbytes].view(dtype)[:n].view(*shape), self.peer_base + off
 
     def barrier(self):
         """Device-side barrier of the two ranks on the current stream: both partials are complete."""
@@ -84,7 +124,7 @@ def exchange(shape, dtype=torch.bfloat16):
         n *= int(s)
     nbytes = n * torch.empty((), dtype=dtype).element_size()
     px = _state["px"]
-    if px is not None and nbytes <= px.slot_bytes:
+    if px is not None and nbytes <= px.slot_bytes and px.arena_bytes >= _state["arena_bytes"]:
         return px
     import torch.distributed as dist
 
@@ -96,7 +136,7 @@ def exchange(shape, dtype=torch.bfloat16):
     new, err = None, None
     try:
         torch.cuda.synchronize()   # nothing still reads the slots that are about to be released
-        new = PeerExchange(pg, nbytes)
+        new = PeerExchange(pg, max(nbytes, px.slot_bytes if px is not None else 0), _state["arena_bytes"])
     except Exception as e:  # no P2P / symmetric memory on this system
         err = e
     ok = torch.tensor([0 if new is None else 1], dtype=torch.int32, device=rt.device())
@@ -108,6 +148,23 @@ def exchange(shape, dtype=torch.bfloat16):
         return None
     _state["px"] = new
     return new
+
+
+def prepare(n_rows: int, d_model: int, n_norms: int):
+    """Called at the start of a forward pass of a model with `n_norms` LayerNorms over (n_rows, d_model)
+    activations: sizes the arena for one step of row-sharded LayerNorm (forward: one bf16 tensor per norm, kept
+    for the backward pass; backward: one bf16 tensor and one stack of partials per norm) and rewinds it."""
+    if not enabled():
+        return None
+    act = (n_rows * d_model * 2 + 255) // 256 * 256
+    part = (2 * 2 * 148 * 2 * 3 * d_model * 4 + 255) // 256 * 256   # [2 ranks][<= 2 blocks per SM, margin x2][3][d] fp32
+    need = n_norms * (2 * act + part) + (1 << 20)
+    if need > _state["arena_bytes"]:
+        _state["arena_bytes"] = need
+    px = exchange((n_rows, d_model))
+    if px is not None:
+        px.step_begin()
+    return px
 
 
 def active() -> bool:

@@ -99,8 +99,11 @@ class Attention(Model):
         px = peer.exchange(out_shape) if (tp and out == "peer") else None
         if px is not None:
             slot, send_ptr, recv_ptr = px.slot("fwd", out_shape)
-            outputs = self.out_projection.forward(att, out="bf16", out_tensor=slot, peer_out=send_ptr)
-            outputs._npt_peer = (px, recv_ptr)
+            n_rows = att.numel() // att.shape[-1]
+            rows = px.rows(n_rows)   # row-sharded LayerNorm: each tile is stored once, on the rank that owns its rows
+            outputs = self.out_projection.forward(att, out="bf16", out_tensor=slot,
+                                                  peer_out=(send_ptr, *px.peer_rows(n_rows)) if rows else send_ptr)
+            outputs._npt_peer, outputs._npt_rows = (px, recv_ptr), rows
             return outputs
         outputs = self.out_projection.forward(att, out="bf16" if out == "peer" else out)
         if tp:
@@ -158,8 +161,11 @@ class Attention(Model):
             px = peer.exchange((*d_qkv.shape[:-1], d_model))
             if px is not None:
                 slot, send_ptr, recv_ptr = px.slot("bwd", (*d_qkv.shape[:-1], d_model))
-                d_in = self.qkv_projection.backward(d_qkv, out="bf16", out_tensor=slot, peer_out=send_ptr)
-                d_in._npt_peer = (px, recv_ptr)
+                n_rows = d_qkv.numel() // d_qkv.shape[-1]
+                rows = px.rows(n_rows)
+                d_in = self.qkv_projection.backward(d_qkv, out="bf16", out_tensor=slot,
+                                                    peer_out=(send_ptr, *px.peer_rows(n_rows)) if rows else send_ptr)
+                d_in._npt_peer, d_in._npt_rows = (px, recv_ptr), rows
                 return d_in
         if out == "peer":
             out = "bf16"

@@ -139,9 +139,11 @@ class OutputEmbedding(Layer):
             px = peer.exchange(shape)
             if px is not None:
                 slot, send_ptr, recv_ptr = px.slot("bwd", shape)
+                n_rows = d_out.numel() // d_out.shape[-1]
+                rows = px.rows(n_rows)
                 d_in = F.linear_backward_input(d_out, self.input_embedding, "embedding", out="bf16", out_tensor=slot,
-                                               peer_out=send_ptr)
-                d_in._npt_peer = (px, recv_ptr)
+                                               peer_out=(send_ptr, *px.peer_rows(n_rows)) if rows else send_ptr)
+                d_in._npt_peer, d_in._npt_rows = (px, recv_ptr), rows
                 return d_in
         d_out = F.linear_backward_input(d_out, self.input_embedding, "embedding", out=out)
         if tp:

@@ -41,8 +41,11 @@ class MLP(Model):
                 # no all-reduce: the partial goes to a peer-visible slot and the LayerNorm that follows adds
                 # the other rank's partial while it reads (distributed/peer.py)
                 slot, send_ptr, recv_ptr = px.slot("fwd", (*inputs.shape[:-1], self.row_linear.weight.data.shape[1]))
-                outputs = self.row_linear.forward(hidden, out="bf16", out_tensor=slot, peer_out=send_ptr)
-                outputs._npt_peer = (px, recv_ptr)
+                n_rows = hidden.numel() // hidden.shape[-1]
+                rows = px.rows(n_rows)   # row-sharded LayerNorm (distributed/peer.py)
+                outputs = self.row_linear.forward(hidden, out="bf16", out_tensor=slot,
+                                                  peer_out=(send_ptr, *px.peer_rows(n_rows)) if rows else send_ptr)
+                outputs._npt_peer, outputs._npt_rows = (px, recv_ptr), rows
                 return outputs
             outputs = self.row_linear.forward(hidden, out="bf16" if out == "peer" else out)
             npdist.all_reduce(outputs, group=npdist.tensor_parallel_group())
@@ -57,8 +60,11 @@ class MLP(Model):
             px = peer.exchange(d_out.shape) if out == "peer" else None
             if px is not None:
                 slot, send_ptr, recv_ptr = px.slot("bwd", (*d_out.shape[:-1], self.column_linear.weight.data.shape[0]))
-                d_in = self.column_linear.backward(d_out, out="bf16", out_tensor=slot, peer_out=send_ptr)
-                d_in._npt_peer = (px, recv_ptr)
+                n_rows = d_out.numel() // d_out.shape[-1]
+                rows = px.rows(n_rows)
+                d_in = self.column_linear.backward(d_out, out="bf16", out_tensor=slot,
+                                                   peer_out=(send_ptr, *px.peer_rows(n_rows)) if rows else send_ptr)
+                d_in._npt_peer, d_in._npt_rows = (px, recv_ptr), rows
                 return d_in
             if out == "peer":
                 out = "bf16"

@@ -4,6 +4,7 @@ from __future__ import annotations
 from functools import partial
 
 from .. import distributed as npdist
+from ..distributed import peer
 from .. import runtime as rt
 from .embedding import InputEmbedding, OutputEmbedding, PositionalEncoding
 from .model import Model
@@ -39,6 +40,9 @@ class Transformer(Model):
     def forward(self, inputs):
         """Model.forward (nn/model.py:15-18).  Without tensor parallelism nothing sits between the embedding
         gather and the positional add, so both run in one kernel (same arithmetic, one pass less)."""
+        if npdist.tensor_parallel_size() > 1:
+            # tp = 2 peer exchange: size / rewind the per-step arena of the row-sharded LayerNorms
+            peer.prepare(inputs.numel(), self.d_model, 2 * self.n_layers)
         if npdist.tensor_parallel_size() > 1 and not self.input_embedding.gathers_full_table(inputs.numel()):
             return super().forward(inputs)
         layers = list(self.layers.values())

@@ -65,7 +65,7 @@ def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_of
          a_strides=(0, 0), b_strides=(0, 0), C_out=None, ldc=0, c_off=0, c_strides=(0, 0),
          Cb_out=None, ldcb=0, cb_off=0, cb_strides=(0, 0), batch=1, batch_inner=1, alpha=1.0,
          bias=None, relu=False, mask=None, ldmask=0, mask_off=0, mask_strides=(0, 0), mode=None,
-         relu_bits_out=None, mask_bits=None, Cb_peer: int = 0, skip_reduce: bool = False):
+         relu_bits_out=None, mask_bits=None, Cb_peer=0, skip_reduce: bool = False):
     """C[b] = alpha * op(A[b]) op(B[b]) (+bias)(ReLU)(*mask>0) — see npt_gemm in the header.
 
     strides are (outer, inner) in elements.  A/B must be fp32 for mode 0 and bf16 for mode 1.
@@ -92,6 +92,8 @@ def gemm(A, B, M, N, K, *, lda, ldb, trans_a=False, trans_b=False, a_off=0, b_of
         g.C_bf16, g.ldcb, g.stride_cb_outer, g.stride_cb_inner = _p(Cb_out, cb_off), ldcb, cb_strides[0], cb_strides[1]
     if Cb_peer:
         assert Cb_out is not None and C_out is None
+        if isinstance(Cb_peer, tuple):   # (address, first row, end row): rows in that range go to the peer ONLY
+            Cb_peer, g.peer_rows_lo, g.peer_rows_hi = Cb_peer
         g.C_bf16_peer = Cb_peer + 2 * cb_off
     g.alpha = alpha
     g.bias = _p(bias)
@@ -212,6 +214,70 @@ def layernorm_bwd(x, gamma, mean, var, dy, eps, want_bf16=False, bf16_only=False
     if colsum_out is not None:
         out._npt_colsum = colsum_out
     return out, dgamma, dbeta
+
+
+def layernorm_fwd_rows(x, x_recv: int, gamma, beta, eps, residual, rows, px):
+    """Row-sharded LayerNorm forward under tp = 2 (distributed/peer.py): `x` holds this rank's partial and
+    `x_recv` (local address) the other rank's, both valid for the rows this rank owns, rows = (first, count).
+    Only those rows are normalised; the bf16 result is written into a peer-visible buffer AND into the other
+    rank's copy of it, so after the caller's barrier both ranks hold every row of it.  Returns
+    (y fp32 [own rows valid] with the full bf16 tensor attached, mean, var, reduced input [own rows valid])."""
+    lib = _lib_()
+    r0, n = rows
+    d = x.shape[-1]
+    T = x.numel() // d
+    assert x.dtype == _BF16 and x.is_contiguous()
+    y = rt.empty(x.shape)
+    yb, yb_peer = px.arena(x.shape, _BF16)
+    mean, var = rt.empty((T,)), rt.empty((T,))
+    x_sum = rt.empty(x.shape, _BF16)
+    e2, e4 = r0 * d * 2, r0 * d * 4
+    with _timed("layernorm_fwd", "hbm", n * d * (2 + 2 + 2 + 4 + 2 + 2 + (4 if residual is not None else 0)) + 8 * n):
+        check(lib.npt_layernorm_fwd_v3(x.data_ptr() + e2, 1, x_recv + e2, x_sum.data_ptr() + e2, _p(gamma), _p(beta),
+                                       (residual.data_ptr() + e4) if residual is not None else None, y.data_ptr() + e4,
+                                       yb.data_ptr() + e2, yb_peer + e2, mean.data_ptr() + 4 * r0, var.data_ptr() + 4 * r0,
+                                       n, d, eps, rt.stream()), "npt_layernorm_fwd_v3")
+    rt.attach_bf16(y, yb)
+    return y, mean, var, x_sum
+
+
+def layernorm_bwd_rows(x_sum, gamma, mean, var, dy, dy_recv: int, eps, rows, px, want_colsum: bool):
+    """Row-sharded LayerNorm backward (see layernorm_fwd_rows): dx (bf16) of the own rows goes to a peer-visible
+    buffer and to the other rank's copy; the per-block dgamma / dbeta / column-sum partials go into this rank's
+    half of a [2][n][slices][d] stack on both ranks.  Returns (dx [complete after the caller's barrier],
+    finish) — `finish()` must be called AFTER that barrier: it returns (dgamma, dbeta, colsum or None), either
+    reduced over both ranks' partials or, inside GraphedTrainStep, as the un-reduced stacks for Adam."""
+    lib = _lib_()
+    r0, n = rows
+    d = x_sum.shape[-1]
+    assert dy.dtype == _BF16 and x_sum.dtype == _BF16
+    dxb, dxb_peer = px.arena(x_sum.shape, _BF16)
+    nsl = 3 if want_colsum else 2
+    nb = int(lib.npt_layernorm_bwd_partials(n, d, 1))
+    stacks, stacks_peer = px.arena((2, nb, nsl, d), _F32)
+    mine = px.rank * nb * nsl * d * 4
+    e2 = r0 * d * 2
+    with _timed("layernorm_bwd", "hbm", n * d * (2 + 2 + 2 + 2 + 2) + 8 * n):
+        check(lib.npt_layernorm_bwd_v4(x_sum.data_ptr() + e2, dy.data_ptr() + e2, 1, dy_recv + e2, _p(gamma), mean.data_ptr() + 4 * r0,
+                                       var.data_ptr() + 4 * r0, None, dxb.data_ptr() + e2, dxb_peer + e2, None, None,
+                                       stacks.data_ptr() if want_colsum else None,   # non-NULL = column sums wanted
+                                       n, d, eps, stacks.data_ptr() + mine, nb * nsl * d * 4, stacks_peer + mine, 1, None,
+                                       rt.stream()), "npt_layernorm_bwd_v4")
+
+    def finish():
+        if rt.defer_wgrad():
+            def slice_(k):
+                t = stacks.view(-1).as_strided((2 * nb, d), (nsl * d, 1), k * d)
+                t._npt_splits, t._npt_split_stride, t._npt_keep = 2 * nb, nsl * d, stacks
+                return t
+            return slice_(0), slice_(1), (slice_(2) if want_colsum else None)
+        dgamma, dbeta = rt.empty((d,)), rt.empty((d,))
+        cs = rt.empty((d,)) if want_colsum else None
+        check(lib.npt_layernorm_bwd_reduce(stacks.data_ptr(), 2 * nb, nsl, d, _p(dgamma), _p(dbeta), _p(cs), rt.stream()),
+              "npt_layernorm_bwd_reduce")
+        return dgamma, dbeta, cs
+
+    return dxb, finish
 
 
 # ---- ReLU / column sum ---------------------------------------------------------------------------

@@ -66,6 +66,9 @@ def main(config, vectors, precision):
     errs["E_final"] = rel_err(E, Z[f"rank{rank}/E_final"])
     errs["E_final_mean_abs_diff"] = float(np.abs(E - Z[f"rank{rank}/E_final"]).mean())
     path = "single" if tp == 1 else ("peer-push" if peer.active() else "nccl")
+    n_rowsplit = sum(1 for b in model.layers.values() for ln in (getattr(b, "norm1", None), getattr(b, "norm2", None))
+                     if ln is not None and getattr(ln, "ran_row_sharded", False))
+    path += f" rowsplit {n_rowsplit}"
     record(f"config_parity[{config}-{precision}]", tp=tp, dp=dp, path=path, **errs)
     print(f"rank {rank} errors {errs} path {path}", flush=True)
     assert errs["logits0"] <= tol_logits and errs["logits0_rowsum"] <= tol_logits, errs

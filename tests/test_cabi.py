@@ -32,7 +32,7 @@ def test_ctypes_table_matches_header():
 
 def test_struct_layouts_match_header():
     # sizes the C compiler gives the two argument structs (LP64): see include/numpitron_b200.h
-    assert C.sizeof(_lib.GemmArgs) == 8 * 4 + 4 * 32 + 8 + 8 + 8 + 8 + 8 + 3 * 8 + 16 + 24 + 8 + 8  # + C_bf16_peer, skip_splitk_reduce (padded)
+    assert C.sizeof(_lib.GemmArgs) == 8 * 4 + 4 * 32 + 8 + 8 + 8 + 8 + 8 + 3 * 8 + 16 + 24 + 8 + 8 + 8  # + C_bf16_peer, peer_rows_lo/hi, skip_splitk_reduce (padded)
     assert C.sizeof(_lib.AdamTensor) == 64 + 16  # + g_splits, g_split_stride
 
 

@@ -72,21 +72,25 @@ CONFIG_WORKER = Path(__file__).resolve().parent / "_nccl_config_worker.py"
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("precision,rowsplit", [("bf16", "1"), ("bf16", "0"), ("fp32", "1")])
 @pytest.mark.parametrize("tp,dp", [(2, 1), (2, 2)])
-def test_c1_shape_vs_oracle_world(tp, dp, precision, tmp_path):
+def test_c1_shape_vs_oracle_world(tp, dp, precision, rowsplit, tmp_path):
     """BASELINE configs[1] shape (L6 d384 H6 ctx256 vocab65) under tp2 (x dp2): 3 training steps, every rank
     against the oracle's emulated world, computed here (a few seconds).  In bf16 mode this is the path
-    SCALE times: GEMM-epilogue peer push + device barrier + reduction inside LayerNorm."""
+    SCALE times: GEMM-epilogue peer push + device barrier + reduction inside LayerNorm — with the rows of every
+    LayerNorm split between the two ranks (rowsplit 1: reduce-scatter / all-gather by push, distributed/peer.py)
+    or both ranks normalising all rows (rowsplit 0)."""
     _need_gpus(tp * dp)
     sys.path.insert(0, str(GOLDEN))
     import make_config_golden as mk
 
     vec = tmp_path / "config_c1.npz"
     mk.main("c1", spec=dict(tp=tp, dp=dp, global_batch=2 * dp, steps=3), out_path=vec)
-    outs = _run_world(CONFIG_WORKER, ["c1", vec, precision], tp * dp, timeout=240)
+    outs = _run_world(CONFIG_WORKER, ["c1", vec, precision], tp * dp, timeout=240, extra_env={"NUMPITRON_TP_ROWSPLIT": rowsplit})
     if precision == "bf16":
         assert "path peer-push" in outs[0] or os.environ.get("NUMPITRON_TP_PEER") == "0", outs[0][-500:]
+        if rowsplit == "1" and os.environ.get("NUMPITRON_TP_PEER") != "0":
+            assert "rowsplit 12" in outs[0], outs[0][-500:]   # every LayerNorm of the 6 blocks ran row-sharded
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
