@@ -42,6 +42,12 @@ int npt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int npt_pinned_alloc(void** out, size_t bytes);
 int npt_pinned_free(void* p);
 int npt_memcpy_async(void* dst, const void* src, size_t bytes, int32_t kind, void* stream);
+/* Device-side barrier of two tensor-parallel ranks on `stream`: `peer_flag` = the flag word in the OTHER rank's
+ * memory (peer pointer), `own_flag` = the same word in local memory, `counter` = a local 8-byte epoch counter
+ * (all zero-initialised; both ranks must execute the same number of barriers).  Replaces the implicit
+ * synchronisation of the reference's blocking Allreduce (distributed/all_reduce.py:23) where the exchange itself
+ * is done by the kernels on either side (npt_gemm_args.C_bf16_peer, npt_layernorm_*_v3/_v4). */
+int npt_peer_barrier(void* peer_flag, void* own_flag, void* counter, void* stream);
 /* device-to-device copy of `rows` rows of `width_bytes` bytes between pitched buffers (re-assembling the vocabulary
  * shards of the tied embedding into one table: nn/embedding.py:19-37 shards it over the vocabulary axis) */
 int npt_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,

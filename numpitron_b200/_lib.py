@@ -62,6 +62,7 @@ _SIGNATURES = {
     "npt_pinned_alloc": (c_int, [C.POINTER(c_void_p), c_size_t]),
     "npt_pinned_free": (c_int, [_P]),
     "npt_memcpy_async": (c_int, [_P, _P, c_size_t, c_int32, _P]),
+    "npt_peer_barrier": (c_int, [_P, _P, _P, _P]),
     "npt_memcpy2d_async": (c_int, [_P, c_size_t, _P, c_size_t, c_size_t, c_size_t, _P]),
     "npt_gemm_workspace_bytes": (c_size_t, [C.POINTER(GemmArgs)]),
     "npt_gemm": (c_int, [C.POINTER(GemmArgs), _P]),

@@ -99,4 +99,38 @@ int npt_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_
   return 0;
 }
 
+// Two-rank device-side barrier on the compute stream (tensor parallelism over peer memory, distributed/peer.py).
+// One thread: epoch = ++(*counter) (local), publish it into the peer's flag, wait until the peer's epoch shows up in
+// ours.  Launched with programmatic dependent launch: it lets its successor start its private prologue at once
+// and itself waits for its predecessor's memory (the tiles / rows that kernel pushed over NVLink) before it signals,
+// so no kernel boundary drains the SMs the way a stream-ordered barrier kernel of another library does.
+}  // extern "C" (kernel below)
+namespace npt {
+__global__ void __launch_bounds__(32) peer_barrier_kernel(unsigned long long* peer_flag, volatile unsigned long long* own_flag,
+                                                           unsigned long long* counter) {
+  pdl_trigger();
+  pdl_wait();   // predecessor complete, its writes (local and peer) performed
+  if (threadIdx.x == 0) {
+    const unsigned long long epoch = *counter + 1;
+    *counter = epoch;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(epoch) : "memory");
+    unsigned long long seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(own_flag) : "memory");
+    } while (seen < epoch);
+    __threadfence_system();
+  }
+}
+}  // namespace npt
+extern "C" {
+
+int npt_peer_barrier(void* peer_flag, void* own_flag, void* counter, void* stream) {
+  NPT_REQUIRE(peer_flag && own_flag && counter, "peer_barrier: null pointer");
+  NPT_CHECK_CUDA(npt::launch_pdl(npt::peer_barrier_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (unsigned long long*)peer_flag,
+                                 (volatile unsigned long long*)own_flag, (unsigned long long*)counter));
+  NPT_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // extern "C"

@@ -50,12 +50,20 @@ class PeerExchange:
         self.slot_bytes = (slot_bytes + 255) // 256 * 256
         self.arena_bytes = (arena_bytes + 255) // 256 * 256
         self.arena_base, self.arena_pos = 8 * self.slot_bytes, 0
-        self.buf = symm.empty(8 * self.slot_bytes + self.arena_bytes, dtype=torch.uint8, device=rt.device())
+        self.flag_off = 8 * self.slot_bytes + self.arena_bytes
+        self.buf = symm.empty(self.flag_off + 256, dtype=torch.uint8, device=rt.device())
         self.hdl = symm.rendezvous(self.buf, pg)
         assert self.hdl.world_size == 2
         self.rank = self.hdl.rank
         self.peer_base = int(self.hdl.buffer_ptrs[1 - self.rank])
         self.counters = {"fwd": 0, "bwd": 0}
+        # own device-side barrier (npt_peer_barrier): one flag word per rank, written by the peer; epoch counter local
+        self.buf[self.flag_off:].zero_()
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=rt.device())
+        torch.cuda.synchronize()
+        self.hdl.barrier(channel=0)      # both flag words are zero before anybody signals
+        torch.cuda.synchronize()
+        self.own_barrier = os.environ.get("NUMPITRON_TP_BARRIER", "torch") == "npt"   # measured: 3.89 ms (npt) vs 3.83 ms (torch) per N=2 step
 
     def slot(self, direction: str, shape, dtype=torch.bfloat16):
         """Next exchange of `direction`: (own: local tensor the GEMM writes its partial to,
@@ -101,7 +109,15 @@ class PeerExchange:
 
     def barrier(self):
         """Device-side barrier of the two ranks on the current stream: both partials are complete."""
-        self.hdl.barrier(channel=0)
+        if self.own_barrier:
+            from .. import _lib
+
+            rc = _lib.load().npt_peer_barrier(self.peer_base + self.flag_off, self.buf.data_ptr() + self.flag_off,
+                                              self.epoch.data_ptr(), rt.stream())
+            if rc:
+                raise _lib.NptError("npt_peer_barrier failed")
+        else:
+            self.hdl.barrier(channel=0)
 
 
 def enabled() -> bool:
