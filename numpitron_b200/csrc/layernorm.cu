@@ -132,6 +132,162 @@ ln_fwd_warp_kernel(const void* __restrict__ x, const void* __restrict__ x_peer, 
   }
 }
 
+// Wide rows (1024 < d <= 8192, d % 4 == 0): one block of 256 threads per row, the row in registers (NV float4
+// per thread), block-wide two-pass statistics.  Same arithmetic as the warp kernel (EXACT = NumPy's rounding).
+template <int NV, bool EXACT>
+__global__ void __launch_bounds__(256)
+ln_fwd_wide_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ residual, float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
+                   float* __restrict__ mean_out, float* __restrict__ var_out, int64_t rows, int d, float eps) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const int nvec = d >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < nvec) {
+      v[i] = ld_stream(xr + c);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float mean = block_sum(s, red) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+      q += (a * a + b * b) + (e * e + f * f);
+    }
+  }
+  const float var = block_sum(q, red) / (float)d;
+  const float denom = sqrtf(var + eps);
+  const float rden = __frcp_rn(denom);
+  if (threadIdx.x == 0) {
+    mean_out[row] = mean;
+    var_out[row] = var;
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  const float4* r4 = residual ? reinterpret_cast<const float4*>(residual + row * d) : nullptr;
+  float4* yr = reinterpret_cast<float4*>(y + row * d);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < nvec) {
+      const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+      float4 o;
+      if (EXACT) {
+        o.x = __fadd_rn(__fmul_rn(g.x, __fdiv_rn(v[i].x - mean, denom)), b.x);
+        o.y = __fadd_rn(__fmul_rn(g.y, __fdiv_rn(v[i].y - mean, denom)), b.y);
+        o.z = __fadd_rn(__fmul_rn(g.z, __fdiv_rn(v[i].z - mean, denom)), b.z);
+        o.w = __fadd_rn(__fmul_rn(g.w, __fdiv_rn(v[i].w - mean, denom)), b.w);
+      } else {
+        o.x = g.x * ((v[i].x - mean) * rden) + b.x;
+        o.y = g.y * ((v[i].y - mean) * rden) + b.y;
+        o.z = g.z * ((v[i].z - mean) * rden) + b.z;
+        o.w = g.w * ((v[i].w - mean) * rden) + b.w;
+      }
+      if (r4) {
+        const float4 r = ld_stream(r4 + c);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      st_stream(yr + c, o);
+      if (yb) st_bf16x4(yb + row * d + (int64_t)c * 4, o);
+    }
+  }
+}
+
+// Wide rows, backward: a block walks rows (grid stride); every thread owns the same 4 * NV columns in every row, so
+// the dgamma / dbeta partials live in its registers and go straight to partial[block][2][d] at the end.
+template <int NV, bool EXACT>
+__global__ void __launch_bounds__(256)
+ln_bwd_wide_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                   const float* __restrict__ var_in, const float* __restrict__ dy, float* __restrict__ dx,
+                   __nv_bfloat16* __restrict__ dxb, float* __restrict__ partial, int64_t rows, int d, float eps) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[32];
+  const int nvec = d >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4 g[NV], ag[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 256;
+    g[i] = (c < nvec) ? __ldg(g4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_d = 1.0f / (float)d;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float mean = mean_in[row], var = var_in[row];
+    float denom = sqrtf(var + eps), stdv = sqrtf(var);   // inputs.std(): no eps (normalization.py:48-50)
+    if (!EXACT) { denom = __frcp_rn(denom); stdv = __frcp_rn(stdv); }
+    const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+    const float4* dr = reinterpret_cast<const float4*>(dy + row * d);
+    float4 xh[NV], w[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = threadIdx.x + i * 256;
+      if (c < nvec) { xh[i] = ld_stream(xr + c); w[i] = ld_stream(dr + c); }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = threadIdx.x + i * 256;
+      if (c < nvec) {
+        float4& h = xh[i];
+        if (EXACT) {
+          h.x = __fdiv_rn(h.x - mean, denom); h.y = __fdiv_rn(h.y - mean, denom);
+          h.z = __fdiv_rn(h.z - mean, denom); h.w = __fdiv_rn(h.w - mean, denom);
+        } else {
+          h.x = (h.x - mean) * denom; h.y = (h.y - mean) * denom; h.z = (h.z - mean) * denom; h.w = (h.w - mean) * denom;
+        }
+        const float4 dd = w[i];
+        ag[i].x += dd.x * h.x; ag[i].y += dd.y * h.y; ag[i].z += dd.z * h.z; ag[i].w += dd.w * h.w;
+        ab[i].x += dd.x; ab[i].y += dd.y; ab[i].z += dd.z; ab[i].w += dd.w;
+        w[i].x = g[i].x * dd.x; w[i].y = g[i].y * dd.y; w[i].z = g[i].z * dd.z; w[i].w = g[i].w * dd.w;
+        s1 += (h.x * w[i].x + h.y * w[i].y) + (h.z * w[i].z + h.w * w[i].w);
+        s2 += (w[i].x + w[i].y) + (w[i].z + w[i].w);
+      }
+    }
+    const float c1 = block_sum(s1, red) * inv_d;
+    const float c2 = block_sum(s2, red) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = threadIdx.x + i * 256;
+      if (c < nvec) {
+        float4 o;
+        if (EXACT) {
+          o.x = __fdiv_rn(w[i].x - c1 * xh[i].x - c2, stdv); o.y = __fdiv_rn(w[i].y - c1 * xh[i].y - c2, stdv);
+          o.z = __fdiv_rn(w[i].z - c1 * xh[i].z - c2, stdv); o.w = __fdiv_rn(w[i].w - c1 * xh[i].w - c2, stdv);
+        } else {
+          o.x = (w[i].x - c1 * xh[i].x - c2) * stdv; o.y = (w[i].y - c1 * xh[i].y - c2) * stdv;
+          o.z = (w[i].z - c1 * xh[i].z - c2) * stdv; o.w = (w[i].w - c1 * xh[i].w - c2) * stdv;
+        }
+        if (dx) st_stream(reinterpret_cast<float4*>(dx + row * d) + c, o);
+        if (dxb) st_bf16x4(dxb + row * d + (int64_t)c * 4, o);
+      }
+    }
+  }
+  float* pg = partial + (size_t)blockIdx.x * 2 * d;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < nvec) {
+      reinterpret_cast<float4*>(pg)[c] = ag[i];
+      reinterpret_cast<float4*>(pg + d)[c] = ab[i];
+    }
+  }
+}
+
 // Any d: one block per row, three passes over the (L1/L2-resident) row.
 __global__ void __launch_bounds__(256)
 ln_fwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
@@ -680,6 +836,20 @@ int npt_layernorm_fwd_v3(const void* x, int32_t x_is_bf16, const void* x_peer, v
       default: return launch_fwd<8>(x, ib, x_peer, x_sum_bf16, gamma, beta, residual, y, y_bf16, y_bf16_peer, mean, var, rows, d, eps, st);
     }
   }
+  if (d % 4 == 0 && d <= 8192 && aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) &&
+      (!residual || aligned16(residual)) && (!y_bf16 || aligned8(y_bf16))) {   // wide rows: block per row, row in registers
+    const int nv = (int)cdiv(d, 1024);
+    const bool exact = y_bf16 == nullptr;   // a bf16 copy is requested only in the bf16 throughput mode
+#define NPT_LN_WIDE(NVV)                                                                                                     \
+    if (exact) NPT_CHECK_CUDA(launch_pdl(ln_fwd_wide_kernel<NVV, true>, dim3((unsigned)rows), dim3(256), 0, st, (const float*)x, gamma, \
+                                         beta, residual, y, (__nv_bfloat16*)y_bf16, mean, var, rows, d, eps));              \
+    else       NPT_CHECK_CUDA(launch_pdl(ln_fwd_wide_kernel<NVV, false>, dim3((unsigned)rows), dim3(256), 0, st, (const float*)x, gamma, \
+                                         beta, residual, y, (__nv_bfloat16*)y_bf16, mean, var, rows, d, eps))
+    if (nv <= 2) { NPT_LN_WIDE(2); } else if (nv <= 4) { NPT_LN_WIDE(4); } else { NPT_LN_WIDE(8); }
+#undef NPT_LN_WIDE
+    NPT_LAUNCH_CHECK();
+    return 0;
+  }
   NPT_CHECK_CUDA(launch_pdl(ln_fwd_block_kernel, dim3((unsigned)rows), dim3(256), 0, st, (const float*)x, gamma, beta, residual, y,
                             (__nv_bfloat16*)y_bf16, mean, var, rows, d, eps));
   NPT_LAUNCH_CHECK();
@@ -795,8 +965,21 @@ int npt_layernorm_bwd_v4(const void* x, const void* dy, int32_t inputs_are_bf16,
   } else {
     int64_t cap = (int64_t)sm_count() * 2;
     nblocks = (int)(rows < cap ? rows : cap);
-    NPT_CHECK_CUDA(launch_pdl(ln_bwd_block_kernel, dim3(nblocks), dim3(256), 0, st, (const float*)x, gamma, mean, var,
-                              (const float*)dy, dx, (__nv_bfloat16*)dx_bf16, partial, rows, d, eps));
+    if (d % 4 == 0 && d <= 8192 && aligned16(x) && aligned16(dy) && aligned16(gamma) && (!dx || aligned16(dx)) &&
+        (!dx_bf16 || aligned8(dx_bf16))) {   // wide rows: column-owning threads, partials in registers
+      const int nv = (int)cdiv(d, 1024);
+      const bool exact = dx_bf16 == nullptr;
+#define NPT_LN_WIDE(NVV)                                                                                                       \
+      if (exact) NPT_CHECK_CUDA(launch_pdl(ln_bwd_wide_kernel<NVV, true>, dim3(nblocks), dim3(256), 0, st, (const float*)x, gamma, mean, \
+                                           var, (const float*)dy, dx, (__nv_bfloat16*)dx_bf16, partial, rows, d, eps));         \
+      else       NPT_CHECK_CUDA(launch_pdl(ln_bwd_wide_kernel<NVV, false>, dim3(nblocks), dim3(256), 0, st, (const float*)x, gamma, mean, \
+                                           var, (const float*)dy, dx, (__nv_bfloat16*)dx_bf16, partial, rows, d, eps))
+      if (nv <= 2) { NPT_LN_WIDE(2); } else if (nv <= 4) { NPT_LN_WIDE(4); } else { NPT_LN_WIDE(8); }
+#undef NPT_LN_WIDE
+    } else {
+      NPT_CHECK_CUDA(launch_pdl(ln_bwd_block_kernel, dim3(nblocks), dim3(256), 0, st, (const float*)x, gamma, mean, var,
+                                (const float*)dy, dx, (__nv_bfloat16*)dx_bf16, partial, rows, d, eps));
+    }
     NPT_LAUNCH_CHECK();
   }
   const int nsl = dxsum ? 3 : 2;

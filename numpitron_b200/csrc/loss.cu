@@ -20,8 +20,26 @@ struct Group {
   __device__ __forceinline__ float max(float v) const { return BLOCK ? block_max(v, red) : warp_max(v); }
 };
 
+// Walks one logits row 128 bits at a time.  V_local is odd for every BASELINE vocabulary (65, 6283, 25129,
+// 50257), so rows start at every alignment: scalar elements up to the first 16-byte boundary, float4 body, scalar
+// tail.  f(v, x) is called for every element (v = column).
+template <typename F>
+__device__ __forceinline__ void ce_row_read(const float* __restrict__ lr, int V, int tid, int n, F f) {
+  int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(lr) & 15u)) & 15u) >> 2);
+  if (head > V) head = V;
+  for (int v = tid; v < head; v += n) f(v, lr[v]);
+  const int nvec = (V - head) >> 2;
+  const float4* p4 = reinterpret_cast<const float4*>(lr + head);
+  for (int i = tid; i < nvec; i += n) {
+    const float4 x = p4[i];
+    const int v = head + 4 * i;
+    f(v, x.x); f(v + 1, x.y); f(v + 2, x.z); f(v + 3, x.w);
+  }
+  for (int v = head + 4 * nvec + tid; v < V; v += n) f(v, lr[v]);
+}
+
 template <bool BLOCK, int STAGE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BLOCK ? 1024 : 256)
 ce_kernel(const float* __restrict__ logits, int64_t ld, const uint16_t* __restrict__ labels,
           float* __restrict__ rowmax, float* __restrict__ picked, float* __restrict__ sumexp,
           float* __restrict__ loss, float* __restrict__ grad, int64_t ldg,
@@ -39,7 +57,7 @@ ce_kernel(const float* __restrict__ logits, int64_t ld, const uint16_t* __restri
   float m;
   if (STAGE == CE_FUSED || STAGE == CE_STAGE1) {
     float mx = -INFINITY;
-    for (int v = tid; v < V; v += n) mx = fmaxf(mx, lr[v]);
+    ce_row_read(lr, V, tid, n, [&](int, float x) { mx = fmaxf(mx, x); });
     m = g.max(mx);
     if (STAGE == CE_STAGE1) {
       if (tid == 0) rowmax[row] = m;
@@ -60,7 +78,7 @@ ce_kernel(const float* __restrict__ logits, int64_t ld, const uint16_t* __restri
   float pk, se;
   if (STAGE == CE_FUSED || STAGE == CE_STAGE2) {
     float s = 0.f;
-    for (int v = tid; v < V; v += n) s += expf(lr[v] - m);
+    ce_row_read(lr, V, tid, n, [&](int, float x) { s += expf(x - m); });
     se = g.sum(s);
     pk = inside ? (lr[label] - m) : 0.f;
     if (STAGE == CE_STAGE2) {
@@ -79,11 +97,51 @@ ce_kernel(const float* __restrict__ logits, int64_t ld, const uint16_t* __restri
   if (tid == 0) loss[row] = __fadd_rn(-pk, logf(se));
   float* gr = grad + row * ldg;
   __nv_bfloat16* gb = gradb ? gradb + row * ldgb : nullptr;
-  for (int v = tid; v < V; v += n) {
-    float p = __fdiv_rn(expf(lr[v] - m), se);
+  auto prob = [&](int v, float x) {
+    float p = __fdiv_rn(expf(x - m), se);
     if (inside && v == label) p = __fsub_rn(p, 1.0f);
-    gr[v] = p;
-    if (gb) gb[v] = __float2bfloat16_rn(p);
+    return p;
+  };
+  if ((reinterpret_cast<uintptr_t>(gr) & 15u) == (reinterpret_cast<uintptr_t>(lr) & 15u)) {
+    // the gradient row has the alignment of the logits row (same pitch): 128-bit loads and stores
+    int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(lr) & 15u)) & 15u) >> 2);
+    if (head > V) head = V;
+    for (int v = tid; v < head; v += n) {
+      const float p = prob(v, lr[v]);
+      gr[v] = p;
+      if (gb) gb[v] = __float2bfloat16_rn(p);
+    }
+    const int nvec = (V - head) >> 2;
+    const float4* p4 = reinterpret_cast<const float4*>(lr + head);
+    float4* g4 = reinterpret_cast<float4*>(gr + head);
+    for (int i = tid; i < nvec; i += n) {
+      const float4 x = p4[i];
+      const int v = head + 4 * i;
+      float4 p;
+      p.x = prob(v, x.x); p.y = prob(v + 1, x.y); p.z = prob(v + 2, x.z); p.w = prob(v + 3, x.w);
+      g4[i] = p;
+      if (gb) {
+        if ((head & 1) == 0) {   // 2 * (head + 4 i) bytes: 4-byte aligned
+          reinterpret_cast<uint32_t*>(gb + v)[0] = pack_bf16(p.x, p.y);
+          reinterpret_cast<uint32_t*>(gb + v)[1] = pack_bf16(p.z, p.w);
+        } else {
+          gb[v] = __float2bfloat16_rn(p.x);
+          *reinterpret_cast<uint32_t*>(gb + v + 1) = pack_bf16(p.y, p.z);
+          gb[v + 3] = __float2bfloat16_rn(p.w);
+        }
+      }
+    }
+    for (int v = head + 4 * nvec + tid; v < V; v += n) {
+      const float p = prob(v, lr[v]);
+      gr[v] = p;
+      if (gb) gb[v] = __float2bfloat16_rn(p);
+    }
+  } else {
+    for (int v = tid; v < V; v += n) {
+      const float p = prob(v, lr[v]);
+      gr[v] = p;
+      if (gb) gb[v] = __float2bfloat16_rn(p);
+    }
   }
   if (gb)  // zero the shadow's padding columns so padded GEMM operands stay clean
     for (int v = V + tid; v < ldgb; v += n) gb[v] = __float2bfloat16_rn(0.f);
@@ -98,7 +156,10 @@ static int launch_ce(const float* logits, int64_t ld, const uint16_t* labels, fl
     NPT_CHECK_CUDA(launch_pdl(ce_kernel<false, STAGE>, dim3((unsigned)cdiv(T, warps)), dim3(warps * 32), 0, st, 
         logits, ld, labels, rowmax, picked, sumexp, loss, grad, ldg, (__nv_bfloat16*)gradb, ldgb, T, V, cs, ce));
   } else {
-    NPT_CHECK_CUDA(launch_pdl(ce_kernel<true, STAGE>, dim3((unsigned)T), dim3(256), 0, st, 
+    // one row per block; wide rows get fat blocks so that few enough rows are in flight for the later passes of the
+    // fused form to find theirs in L2 (1184 rows x 201 KB at 256 threads did not fit the 126 MB)
+    const int threads = V >= 16384 ? 1024 : (V >= 4096 ? 512 : 256);
+    NPT_CHECK_CUDA(launch_pdl(ce_kernel<true, STAGE>, dim3((unsigned)T), dim3(threads), 0, st, 
         logits, ld, labels, rowmax, picked, sumexp, loss, grad, ldg, (__nv_bfloat16*)gradb, ldgb, T, V, cs, ce));
   }
   NPT_LAUNCH_CHECK();

@@ -332,7 +332,8 @@ def test_layernorm_golden(golden_layers):
     close(host(db), G["ln/db"], 1e-5)
 
 
-@pytest.mark.parametrize("rows,d", [(1, 4), (77, 384), (1000, 768), (33, 1024), (19, 130), (5, 4096), (4099, 384)])
+@pytest.mark.parametrize("rows,d", [(1, 4), (77, 384), (1000, 768), (33, 1024), (19, 130), (5, 4096), (4099, 384),
+                                    (700, 2048), (300, 4096), (50, 8192), (9, 1028), (3, 8196)])   # wide rows: block-per-row kernels
 def test_layernorm_shapes_vs_oracle(rows, d):
     rng = np.random.default_rng(d + rows)
     x = (1.5 + 0.03 * rng.standard_normal((1, rows, d))).astype(np.float32)   # large mean, small std (Q12)
