@@ -788,11 +788,201 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, S = 256 (two 128-row tiles), Dh = 64: ONE kernel for dQ, dK and dV.
+// The split dkv / dq kernels above recompute S and dP (and the exponentials, the expensive part: MUFU-bound) for
+// every (query tile, key tile) pair twice, once per kernel.  With two tiles per sequence the whole causal
+// problem of a (batch, head) fits one CTA: item = (b, head); steps = the three live pairs (i, j) =
+// (0,0), (1,0), (1,1); per pair S, dP -> P, dS (once) -> dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j.
+// TMEM: S | dP | dK | dV | dQ_0 | dQ_1 = 128 + 128 + 4 x 64 = 512 columns.  Every operand tile is loaded once per
+// item (8 tiles, 128 KB) and released as soon as its last pair is done, so the next item's loads run under
+// this item's later pairs.  15 tile GEMMs and 3 softmax-backward tiles per item instead of 21 and 6.
+// ------------------------------------------------------------------------------------------------
+struct AttnBwd2Smem {
+  static constexpr int T = AttnCfg<64>::TILE;   // 16 KB
+  // tile ids: 0 Q0, 1 Q1, 2 dO0, 3 dO1, 4 K0, 5 K1, 6 V0, 7 V1
+  static constexpr int TILES = 0, P = 8 * T, DS = P + AT_PTILE, BAR = DS + AT_PTILE;
+  static constexpr int TOTAL = BAR + 32 * 8 + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_s256_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                     const float* __restrict__ lse, const float* __restrict__ D, __nv_bfloat16* __restrict__ dqkv,
+                     int B, int h, float inv_div) {
+  constexpr int DH = 64, S = 256;
+  using L = AttnBwd2Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+  uint64_t *full = bars, *empty = bars + 8, *s_full = bars + 16, *s_empty = bars + 17, *pds_full = bars + 18,
+           *acc_done = bars + 19, *kv_out_done = bars + 20, *out_done = bars + 21;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = B * h;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    for (int i = 0; i < 8; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(pds_full, 4);
+    mbar_init(acc_done, 1);
+    mbar_init(kv_out_done, 4);
+    mbar_init(out_done, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t tmem_S = tmem, tmem_dP = tmem + 128, tmem_dK = tmem + 256, tmem_dV = tmem + 320, tmem_dQ0 = tmem + 384,
+                 tmem_dQ1 = tmem + 448;
+  auto tile = [&](int id) { return smem + L::TILES + id * L::T; };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t wi = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++wi) {
+        const int b = w / h, hh = w - b * h;
+        const int col_q = hh * 3 * DH, row0 = b * S;
+        const uint32_t ph = (wi & 1) ^ 1;
+        // in the order the pairs need them: (0,0): Q0 K0 dO0 V0; (1,0): Q1 dO1; (1,1): K1 V1
+        auto load = [&](int id, const CUtensorMap* map, int col, int row) {
+          mbar_wait(empty + id, ph);
+          mbar_expect_tx(full + id, L::T);
+          load_tile<DH>(map, full + id, tile(id), col, row);
+        };
+        load(0, &tmQKV, col_q, row0);
+        load(4, &tmQKV, col_q + DH, row0);
+        load(2, &tmDO, hh * DH, row0);
+        load(6, &tmQKV, col_q + 2 * DH, row0);
+        load(1, &tmQKV, col_q, row0 + 128);
+        load(3, &tmDO, hh * DH, row0 + 128);
+        load(5, &tmQKV, col_q + DH, row0 + 128);
+        load(7, &tmQKV, col_q + 2 * DH, row0 + 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(128, false, false);  // S = Q K^T, dP = dO V^T
+      constexpr uint32_t idesc_a = make_idesc(DH, true, true);     // dV = P^T dO, dK = dS^T Q
+      constexpr uint32_t idesc_q = make_idesc(DH, false, true);    // dQ = dS K
+      const uint32_t sp = smem_u32(smem + L::P), sds = smem_u32(smem + L::DS);
+      const int n_items = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const uint32_t n_steps = (uint32_t)n_items * 3;
+      // pair p of an item: query tile i, key tile j
+      auto issue_sdp = [&](uint32_t t) {
+        const uint32_t wi = t / 3, p = t - wi * 3, ph = wi & 1;
+        const int i = p == 0 ? 0 : 1, j = p == 2 ? 1 : 0;
+        if (p == 0) { mbar_wait(full + 0, ph); mbar_wait(full + 4, ph); mbar_wait(full + 2, ph); mbar_wait(full + 6, ph); }
+        if (p == 1) { mbar_wait(full + 1, ph); mbar_wait(full + 3, ph); }
+        if (p == 2) { mbar_wait(full + 5, ph); mbar_wait(full + 7, ph); }
+        mbar_wait(s_empty, (t & 1) ^ 1);   // the threads have read S / dP of the previous step
+        fence_after();
+        const uint32_t tq = smem_u32(tile(i)), tdo = smem_u32(tile(2 + i)), tk = smem_u32(tile(4 + j)), tv = smem_u32(tile(6 + j));
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, desc_k<DH>(tq, k), desc_k<DH>(tk, k), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_dP, desc_k<DH>(tdo, k), desc_k<DH>(tv, k), idesc_s, k > 0);
+        umma_commit(s_full);
+      };
+      if (n_steps > 0) issue_sdp(0);
+      for (uint32_t t = 0; t < n_steps; ++t) {
+        const uint32_t wi = t / 3, p = t - wi * 3;
+        const int i = p == 0 ? 0 : 1, j = p == 2 ? 1 : 0;
+        mbar_wait(pds_full, t & 1);                 // P / dS of this step are in shared memory (S / dP drained)
+        if (t + 1 < n_steps) issue_sdp(t + 1);      // next score tiles first: the threads are waiting for them
+        if (p == 0) mbar_wait(out_done, (wi & 1) ^ 1);   // the previous item's accumulators were read out
+        if (p == 2) mbar_wait(kv_out_done, wi & 1);      // dK_0 / dV_0 were read out: the columns take dK_1 / dV_1
+        fence_after();
+        const uint64_t dpt = make_smem_desc(sp, 16384, 1024), ddst = make_smem_desc(sds, 16384, 1024);
+        const uint32_t tq = smem_u32(tile(i)), tdo = smem_u32(tile(2 + i)), tk = smem_u32(tile(4 + j));
+        const uint32_t tdq = i == 0 ? tmem_dQ0 : tmem_dQ1;
+        const bool acc_kv = p == 1, acc_q = p == 2;     // (1,0) adds to dK_0 / dV_0; (1,1) adds to dQ_1
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dV, dpt + (uint64_t)(k * 128), desc_mn<DH>(tdo, k), idesc_a, (acc_kv || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16(tmem_dK, ddst + (uint64_t)(k * 128), desc_mn<DH>(tq, k), idesc_a, (acc_kv || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t dds = make_smem_desc(sds + (k >> 2) * 16384, 16, 1024) + (uint64_t)((k & 3) * 2);
+          umma_bf16(tdq, dds, desc_mn<DH>(tk, k), idesc_q, (acc_q || k > 0));
+        }
+        umma_commit(acc_done);
+        // operand tiles whose last pair this was go back to the producer
+        if (p == 0) { umma_commit(empty + 0); umma_commit(empty + 2); }
+        if (p == 1) { umma_commit(empty + 4); umma_commit(empty + 6); }
+        if (p == 2) { umma_commit(empty + 1); umma_commit(empty + 3); umma_commit(empty + 5); umma_commit(empty + 7); }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t sP = smem_u32(smem + L::P), sdS = smem_u32(smem + L::DS);
+    uint32_t t = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int b = w / h, hh = w - b * h;
+      float lse_r = 0.f, D_r = 0.f;
+#pragma unroll 1
+      for (int p = 0; p < 3; ++p, ++t) {
+        const int i = p == 0 ? 0 : 1, j = p == 2 ? 1 : 0;
+        if (p < 2) {   // first pair of query tile i: its row statistics
+          const int64_t stat = ((int64_t)b * h + hh) * S + i * 128 + row;
+          lse_r = lse[stat];
+          D_r = D[stat];
+        }
+        mbar_wait(s_full, t & 1);
+        fence_after();
+        // P / dS tiles are free once the previous step's accumulate MMAs retired
+        bwd_rows<true>(tmem_S + lane_addr, tmem_dP + lane_addr, row, i == j, lse_r, D_r, inv_div, sP, sdS,
+                       t > 0 ? acc_done : nullptr, (t - 1) & 1);
+        fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(pds_full); }
+        // accumulators that are complete after this pair
+        mbar_wait(acc_done, t & 1);
+        fence_after();
+        const int64_t q_glob = (int64_t)b * S + i * 128 + row, k_glob = (int64_t)b * S + j * 128 + row;
+        if (p == 0) {
+          store_acc_row<DH>(tmem_dQ0 + lane_addr, dqkv + (q_glob * h + hh) * 3 * DH);
+        } else {
+          __nv_bfloat16* kbase = dqkv + (k_glob * h + hh) * 3 * DH;
+          store_acc_row<DH>(tmem_dK + lane_addr, kbase + DH);
+          store_acc_row<DH>(tmem_dV + lane_addr, kbase + 2 * DH);
+          if (p == 2) store_acc_row<DH>(tmem_dQ1 + lane_addr, dqkv + (q_glob * h + hh) * 3 * DH);
+          fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p == 1 ? kv_out_done : out_done);
+        }
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
 static int check_shape(const char* who, int B, int S, int h, int Dh) {
   NPT_REQUIRE(B > 0 && h > 0, "%s: bad shape", who);
   NPT_REQUIRE(Dh == 64 || Dh == 96, "%s: fused attention supports head_dim 64 and 96 (got %d); use the GEMM + softmax path", who, Dh);
   NPT_REQUIRE(S > 0 && S % 128 == 0, "%s: fused attention needs seq_len %% 128 == 0 (got %d)", who, S);
   return 0;
+}
+
+static bool attn_bwd_force_split() {   // NUMPITRON_ATTN_BWD=split: the dkv + dq kernels at every shape (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NUMPITRON_ATTN_BWD"); v = (e && e[0] == 's') ? 1 : 0; }
+  return v == 1;
 }
 
 static int persistent_grid(int items) {
@@ -838,8 +1028,19 @@ static int attention_bwd_t(const void* qkv_bf16, const void* out_bf16, const voi
     NPT_CHECK_CUDA(cudaFuncSetAttribute(kdq, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem<DH>::TOTAL));
     attr = true;
   }
-  const int grid = persistent_grid(B * h * (S / 128));
   const float inv_div = 1.0f / divisor;
+  if (DH == 64 && S == 256 && !attn_bwd_force_split()) {   // both tiles of a sequence in one CTA: dQ, dK, dV in one pass
+    static bool attr2 = false;
+    if (!attr2) {
+      NPT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_s256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwd2Smem::TOTAL));
+      attr2 = true;
+    }
+    NPT_CHECK_CUDA(launch_pdl(attn_bwd_s256_kernel, dim3(persistent_grid(B * h)), dim3(AT_THREADS), AttnBwd2Smem::TOTAL, st, tmQKV,
+                              tmDO, lse, (const float*)D, (__nv_bfloat16*)dqkv_bf16, B, h, inv_div));
+    NPT_LAUNCH_CHECK();
+    return 0;
+  }
+  const int grid = persistent_grid(B * h * (S / 128));
   NPT_CHECK_CUDA(launch_pdl(kdkv, dim3(grid), dim3(AT_THREADS), AttnDkvSmem<DH>::TOTAL, st, tmQKV, tmDO, lse, (const float*)D,
                             (__nv_bfloat16*)dqkv_bf16, B, S, h, inv_div));
   NPT_LAUNCH_CHECK();
