@@ -926,6 +926,24 @@ attn_bwd_s256_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t sP = smem_u32(smem + L::P), sdS = smem_u32(smem + L::DS);
     uint32_t t = 0;
+    // The accumulators a pair completes are read out at the START of the next step, behind the acc_done wait that
+    // step needs anyway before it overwrites the P / dS tiles — never as a wait of their own.
+    int pend_p = -1, pend_b = 0, pend_hh = 0;
+    auto read_out = [&]() {   // after acc_done of the pending step was observed
+      const int i = pend_p == 0 ? 0 : 1, j = pend_p == 2 ? 1 : 0;
+      const int64_t q_glob = (int64_t)pend_b * S + i * 128 + row, k_glob = (int64_t)pend_b * S + j * 128 + row;
+      if (pend_p == 0) {
+        store_acc_row<DH>(tmem_dQ0 + lane_addr, dqkv + (q_glob * h + pend_hh) * 3 * DH);
+      } else {
+        __nv_bfloat16* kbase = dqkv + (k_glob * h + pend_hh) * 3 * DH;
+        store_acc_row<DH>(tmem_dK + lane_addr, kbase + DH);
+        store_acc_row<DH>(tmem_dV + lane_addr, kbase + 2 * DH);
+        if (pend_p == 2) store_acc_row<DH>(tmem_dQ1 + lane_addr, dqkv + (q_glob * h + pend_hh) * 3 * DH);
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pend_p == 1 ? kv_out_done : out_done);
+      }
+    };
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int b = w / h, hh = w - b * h;
       float lse_r = 0.f, D_r = 0.f;
@@ -937,31 +955,25 @@ attn_bwd_s256_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           lse_r = lse[stat];
           D_r = D[stat];
         }
+        if (pend_p >= 0) {   // previous step: its accumulate MMAs retired -> P / dS tiles are free, its outputs complete
+          mbar_wait(acc_done, (t - 1) & 1);
+          fence_after();
+          read_out();
+        }
         mbar_wait(s_full, t & 1);
         fence_after();
-        // P / dS tiles are free once the previous step's accumulate MMAs retired
-        bwd_rows<true>(tmem_S + lane_addr, tmem_dP + lane_addr, row, i == j, lse_r, D_r, inv_div, sP, sdS,
-                       t > 0 ? acc_done : nullptr, (t - 1) & 1);
+        bwd_rows<true>(tmem_S + lane_addr, tmem_dP + lane_addr, row, i == j, lse_r, D_r, inv_div, sP, sdS, nullptr, 0);
         fence_before();
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(pds_full); }
-        // accumulators that are complete after this pair
-        mbar_wait(acc_done, t & 1);
-        fence_after();
-        const int64_t q_glob = (int64_t)b * S + i * 128 + row, k_glob = (int64_t)b * S + j * 128 + row;
-        if (p == 0) {
-          store_acc_row<DH>(tmem_dQ0 + lane_addr, dqkv + (q_glob * h + hh) * 3 * DH);
-        } else {
-          __nv_bfloat16* kbase = dqkv + (k_glob * h + hh) * 3 * DH;
-          store_acc_row<DH>(tmem_dK + lane_addr, kbase + DH);
-          store_acc_row<DH>(tmem_dV + lane_addr, kbase + 2 * DH);
-          if (p == 2) store_acc_row<DH>(tmem_dQ1 + lane_addr, dqkv + (q_glob * h + hh) * 3 * DH);
-          fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(p == 1 ? kv_out_done : out_done);
-        }
+        pend_p = p; pend_b = b; pend_hh = hh;
       }
+    }
+    if (pend_p >= 0) {
+      mbar_wait(acc_done, (t - 1) & 1);
+      fence_after();
+      read_out();
     }
   }
   fence_before();

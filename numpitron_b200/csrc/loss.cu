@@ -158,7 +158,7 @@ static int launch_ce(const float* logits, int64_t ld, const uint16_t* labels, fl
   } else {
     // one row per block; wide rows get fat blocks so that few enough rows are in flight for the later passes of the
     // fused form to find theirs in L2 (1184 rows x 201 KB at 256 threads did not fit the 126 MB)
-    const int threads = V >= 16384 ? 1024 : (V >= 4096 ? 512 : 256);
+    const int threads = V >= 16384 ? 1024 : 256;   // (512 threads at V = 6283 measured slower than 256: 503 vs 470 us)
     NPT_CHECK_CUDA(launch_pdl(ce_kernel<true, STAGE>, dim3((unsigned)T), dim3(threads), 0, st, 
         logits, ld, labels, rowmax, picked, sumexp, loss, grad, ldg, (__nv_bfloat16*)gradb, ldgb, T, V, cs, ce));
   }
