@@ -310,6 +310,7 @@ def profile_eager_step(step, model, opt, batch, ms_per_step, precision):
     import torch
 
     from numpitron_b200 import ops
+    from numpitron_b200 import runtime as rt
     from numpitron_b200.train import train_step_device
 
     ops.PROFILE = []
@@ -320,7 +321,8 @@ def profile_eager_step(step, model, opt, batch, ms_per_step, precision):
             # queued when the GPU reaches it: the event pairs then bracket pure kernel time (no host-latency
             # gaps), with the step's real cache state.
             torch.cuda._sleep(16_000_000)
-            train_step_device(model, opt, *batch)
+            with rt.deferred_wgrad():   # the launches of the graphed step (split-K / LayerNorm partials go to Adam un-reduced)
+                train_step_device(model, opt, *batch)
     step.stream.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     for p in prof:

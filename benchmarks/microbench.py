@@ -74,7 +74,7 @@ def bench_linear(T, d, mode):
     dy = torch.randn(T, d, device="cuda").to(dt)
     y, dx, dw = rt.empty((T, d)), rt.empty((T, d)), rt.empty((d, d))
     flops = 2.0 * T * d * d
-    name = "linear_bf16" if mode == 1 else "linear_fp32"
+    name = {0: "linear_fp32_ffma", 1: "linear_bf16", 2: "linear_fp32_3xtf32"}[mode]
     s = timeit(lambda: ops.gemm(x, w, T, d, d, lda=d, ldb=d, C_out=y, ldc=d, mode=mode), flush=False)
     emit(name + "_fwd_NN", {"T": T, "d": d}, s, flops=flops)
     s = timeit(lambda: ops.gemm(dy, w, T, d, d, lda=d, ldb=d, trans_b=True, C_out=dx, ldc=d, mode=mode), flush=False)
@@ -151,6 +151,8 @@ def main():
             bench_linear(8 * S, d, 1)
     for d in [384, 1024]:
         bench_linear(8 * 256, d, 0)
+    for d in ds:                       # the fp32-accurate mode: 3xTF32 on the tensor cores
+        bench_linear(8 * 1024, d, 2)
     for d in ds:
         for S in seqs:
             bench_attention(8, S, d)

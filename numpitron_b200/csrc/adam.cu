@@ -35,12 +35,19 @@ __device__ __forceinline__ float4 adam_grad4(const npt_adam_tensor& t, int64_t i
   const float4* g0 = reinterpret_cast<const float4*>(t.g) + i4;
   const int64_t st4 = t.g_split_stride >> 2;  // the vector path requires a stride that is a multiple of 4
   int64_t s = 0;
-  for (; s + 8 <= t.g_splits; s += 8) {  // eight independent loads in flight, additions in split order
-    float4 a[8];
+  for (; s + 16 <= t.g_splits; s += 16) {  // sixteen independent loads in flight (the LayerNorm partial stacks are ~300 deep)
+    float4 a[16];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] = ld_stream(g0 + (s + k) * st4);
+    for (int k = 0; k < 16; ++k) a[k] = ld_stream(g0 + (s + k) * st4);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { acc.x += a[k].x; acc.y += a[k].y; acc.z += a[k].z; acc.w += a[k].w; }
+    for (int k = 0; k < 16; ++k) { acc.x += a[k].x; acc.y += a[k].y; acc.z += a[k].z; acc.w += a[k].w; }
+  }
+  for (; s + 4 <= t.g_splits; s += 4) {  // additions in split order throughout
+    float4 a[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = ld_stream(g0 + (s + k) * st4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { acc.x += a[k].x; acc.y += a[k].y; acc.z += a[k].z; acc.w += a[k].w; }
   }
   for (; s < t.g_splits; ++s) {
     const float4 a = ld_stream(g0 + s * st4);

@@ -56,7 +56,17 @@ splitk_reduce_kernel(const float* __restrict__ partial, GemmEpilogue e, int spli
         const int64_t r = i - (int64_t)b * mn;
         const int m = (int)(r / e.N), n = (int)(r - (int64_t)m * e.N);
         float acc = 0.f;
-        for (int s = 0; s < splits; ++s) acc += partial[((int64_t)s * batch) * mn + i];
+        const float* p0 = partial + i;
+        const int64_t stride = (int64_t)batch * mn;
+        int s = 0;
+        for (; s + 8 <= splits; s += 8) {   // eight independent loads in flight, additions in split order
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __ldcs(p0 + (int64_t)(s + u) * stride);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+        for (; s < splits; ++s) acc += __ldcs(p0 + (int64_t)s * stride);
         epi_store1(e, b, m, n, acc);
       }
     }

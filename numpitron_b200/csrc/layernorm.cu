@@ -664,7 +664,7 @@ ln_bwd_block_kernel(const float* __restrict__ x, const float* __restrict__ gamma
   }
 }
 
-// Stage 2: out[c] = ((0 + partial[0][c]) + partial[1][c]) + ...  — block order, one thread per column, eight
+// Stage 2: out[c] = ((0 + partial[0][c]) + partial[1][c]) + ...  — block order, one thread per column, sixteen
 // loads in flight.  The same additions in the same order as the fused Adam kernel performs when the partials
 // are handed to it un-reduced (npt_adam_tensor.g_splits), so both routes give identical bits.
 __global__ void __launch_bounds__(128)
@@ -678,12 +678,12 @@ reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ ou
   const float* src = partial + c;
   float acc = 0.f;
   int b = 0;
-  for (; b + 8 <= nblocks; b += 8) {
-    float v[8];
+  for (; b + 16 <= nblocks; b += 16) {
+    float v[16];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = src[(size_t)(b + k) * pitch];
+    for (int k = 0; k < 16; ++k) v[k] = src[(size_t)(b + k) * pitch];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += v[k];
+    for (int k = 0; k < 16; ++k) acc += v[k];
   }
   for (; b < nblocks; ++b) acc += src[(size_t)b * pitch];
   if (c < d) out0[c] = acc; else if (c < 2 * d) out1[c - d] = acc; else out2[c - 2 * d] = acc;

@@ -83,6 +83,9 @@ class Adam:
                 g = g.contiguous()
             shadow = lyr._shadows.get(name) if rt.is_bf16() else None
             entries.append((p.data, g, state.momentum.data, state.velocity.data, shadow))
+        # blocks are scheduled in table order: the tensors whose gradient is a deep stack of partials (LayerNorm /
+        # bias gradients handed over un-reduced) take longest per element, so they go first and overlap the bulk
+        entries.sort(key=lambda e: -getattr(e[1], "_npt_splits", 1))
         table = self._table_for(entries)
         t = self.timestep
         ops.adam_step(table,_f32(self.learning_rate), _f32(self.beta1), _f32(1 - self.beta1),
