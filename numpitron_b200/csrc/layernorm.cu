@@ -489,6 +489,7 @@ ln_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
                      float* __restrict__ partial, float* __restrict__ partial_peer, int64_t rows, int d, float eps, int R) {
   constexpr int NT = PEER ? 3 : 2;       // row tensors per slot: x, dy (, the other rank's dy)
   constexpr int NSL = DXSUM ? 3 : 2;
+  constexpr bool TWO_PASS = NV >= 5;     // rows wider than 512 columns: two passes over the slot (see below)
   extern __shared__ __align__(16) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = d >> 2;
@@ -548,50 +549,90 @@ ln_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
       } while (!done);
     }
     const uint32_t base = ln_smem_u32(ring + (size_t)slot * NT * row_bytes);
-    float4 xh[NV], w[NV];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + i * 32;
-      if (c < nvec) {
-        float4 xv = ln_lds_bf16x4(base + c * 8);
-        float4 dd = ln_lds_bf16x4(base + row_bytes + c * 8);
-        if (PEER) {
-          const float4 pp = ln_lds_bf16x4(base + 2 * row_bytes + c * 8);
-          dd.x = __bfloat162float(__float2bfloat16_rn(dd.x + pp.x)); dd.y = __bfloat162float(__float2bfloat16_rn(dd.y + pp.y));
-          dd.z = __bfloat162float(__float2bfloat16_rn(dd.z + pp.z)); dd.w = __bfloat162float(__float2bfloat16_rn(dd.w + pp.w));
-        }
-        xv.x = (xv.x - mean) * rden; xv.y = (xv.y - mean) * rden; xv.z = (xv.z - mean) * rden; xv.w = (xv.w - mean) * rden;
-        ag[i].x += dd.x * xv.x; ag[i].y += dd.y * xv.y; ag[i].z += dd.z * xv.z; ag[i].w += dd.w * xv.w;
-        ab[i].x += dd.x; ab[i].y += dd.y; ab[i].z += dd.z; ab[i].w += dd.w;
-        const float4 gv = g[i];
-        dd.x *= gv.x; dd.y *= gv.y; dd.z *= gv.z; dd.w *= gv.w;   // gamma * dy
-        s1 += (xv.x * dd.x + xv.y * dd.y) + (xv.z * dd.z + xv.w * dd.w);
-        s2 += (dd.x + dd.y) + (dd.z + dd.w);
-        xh[i] = xv; w[i] = dd;
+    // x-hat and gamma * dy of 4 columns, from the row slot
+    auto load4 = [&](int c, float4& xv, float4& dd, float4& wv) {
+      xv = ln_lds_bf16x4(base + c * 8);
+      dd = ln_lds_bf16x4(base + row_bytes + c * 8);
+      if (PEER) {
+        const float4 pp = ln_lds_bf16x4(base + 2 * row_bytes + c * 8);
+        dd.x = __bfloat162float(__float2bfloat16_rn(dd.x + pp.x)); dd.y = __bfloat162float(__float2bfloat16_rn(dd.y + pp.y));
+        dd.z = __bfloat162float(__float2bfloat16_rn(dd.z + pp.z)); dd.w = __bfloat162float(__float2bfloat16_rn(dd.w + pp.w));
       }
-    }
-    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
-    // every lane's shared-memory reads fed the shuffles above: the slot can be refilled
-    if (lane == 0 && row + (int64_t)R * stride < rows) issue(slot, row + (int64_t)R * stride);
-    if (++slot == R) { slot = 0; phase ^= 1; }
+      xv.x = (xv.x - mean) * rden; xv.y = (xv.y - mean) * rden; xv.z = (xv.z - mean) * rden; xv.w = (xv.w - mean) * rden;
+      const float4 gv = TWO_PASS ? __ldg(g4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      wv = dd;
+      if (TWO_PASS) { wv.x *= gv.x; wv.y *= gv.y; wv.z *= gv.z; wv.w *= gv.w; }
+    };
+    auto emit4 = [&](int c, const float4& xv, const float4& wv, float c1, float c2) {
+      float4 o;
+      o.x = (wv.x - c1 * xv.x - c2) * rstd;
+      o.y = (wv.y - c1 * xv.y - c2) * rstd;
+      o.z = (wv.z - c1 * xv.z - c2) * rstd;
+      o.w = (wv.w - c1 * xv.w - c2) * rstd;
+      if (dx) st_stream(reinterpret_cast<float4*>(dx + row * d) + c, o);
+      if (dxb) st_bf16x4(dxb + row * d + (int64_t)c * 4, o);
+      if (PEER && dxb_peer) st_bf16x4(dxb_peer + row * d + (int64_t)c * 4, o);   // all-gather by push
+      if (DXSUM) {
+        float4 t = dsum[c];
+        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+        dsum[c] = t;
+      }
+    };
+    float s1 = 0.f, s2 = 0.f;
+    if (TWO_PASS) {
+      // Wide rows (NV >= 5): holding x-hat and gamma * dy of the whole row next to the dgamma / dbeta accumulators
+      // costs 157+ registers = one block per SM.  The row sits in shared memory anyway: pass 1 accumulates, pass 2
+      // reads it again for dx; gamma comes from L1 instead of registers.  ~100 registers, two blocks per SM.
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + i * 32;
-      if (c < nvec) {
-        float4 o;
-        o.x = (w[i].x - c1 * xh[i].x - c2) * rstd;
-        o.y = (w[i].y - c1 * xh[i].y - c2) * rstd;
-        o.z = (w[i].z - c1 * xh[i].z - c2) * rstd;
-        o.w = (w[i].w - c1 * xh[i].w - c2) * rstd;
-        if (dx) st_stream(reinterpret_cast<float4*>(dx + row * d) + c, o);
-        if (dxb) st_bf16x4(dxb + row * d + (int64_t)c * 4, o);
-        if (PEER && dxb_peer) st_bf16x4(dxb_peer + row * d + (int64_t)c * 4, o);   // all-gather by push
-        if (DXSUM) {
-          float4 t = dsum[c];
-          t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
-          dsum[c] = t;
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + i * 32;
+        if (c < nvec) {
+          float4 xv, dd, wv;
+          load4(c, xv, dd, wv);
+          ag[i].x += dd.x * xv.x; ag[i].y += dd.y * xv.y; ag[i].z += dd.z * xv.z; ag[i].w += dd.w * xv.w;
+          ab[i].x += dd.x; ab[i].y += dd.y; ab[i].z += dd.z; ab[i].w += dd.w;
+          s1 += (xv.x * wv.x + xv.y * wv.y) + (xv.z * wv.z + xv.w * wv.w);
+          s2 += (wv.x + wv.y) + (wv.z + wv.w);
         }
+      }
+      const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + i * 32;
+        if (c < nvec) {
+          float4 xv, dd, wv;
+          load4(c, xv, dd, wv);
+          emit4(c, xv, wv, c1, c2);
+        }
+      }
+      __syncwarp();   // every lane is done with the slot: it can be refilled
+      if (lane == 0 && row + (int64_t)R * stride < rows) issue(slot, row + (int64_t)R * stride);
+      if (++slot == R) { slot = 0; phase ^= 1; }
+    } else {
+      float4 xh[NV], w[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + i * 32;
+        if (c < nvec) {
+          float4 xv, dd, wv;
+          load4(c, xv, dd, wv);
+          ag[i].x += dd.x * xv.x; ag[i].y += dd.y * xv.y; ag[i].z += dd.z * xv.z; ag[i].w += dd.w * xv.w;
+          ab[i].x += dd.x; ab[i].y += dd.y; ab[i].z += dd.z; ab[i].w += dd.w;
+          const float4 gv = g[i];
+          wv.x = gv.x * dd.x; wv.y = gv.y * dd.y; wv.z = gv.z * dd.z; wv.w = gv.w * dd.w;   // gamma * dy
+          s1 += (xv.x * wv.x + xv.y * wv.y) + (xv.z * wv.z + xv.w * wv.w);
+          s2 += (wv.x + wv.y) + (wv.z + wv.w);
+          xh[i] = xv; w[i] = wv;
+        }
+      }
+      const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+      // every lane's shared-memory reads fed the shuffles above: the slot can be refilled
+      if (lane == 0 && row + (int64_t)R * stride < rows) issue(slot, row + (int64_t)R * stride);
+      if (++slot == R) { slot = 0; phase ^= 1; }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + i * 32;
+        if (c < nvec) emit4(c, xh[i], w[i], c1, c2);
       }
     }
   }
