@@ -807,8 +807,8 @@ struct AttnBwd2Smem {
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_s256_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                     const float* __restrict__ lse, const float* __restrict__ D, __nv_bfloat16* __restrict__ dqkv,
-                     int B, int h, float inv_div) {
+                     const float* __restrict__ lse, const __nv_bfloat16* __restrict__ o_fwd, const __nv_bfloat16* __restrict__ d_o,
+                     __nv_bfloat16* __restrict__ dqkv, int B, int h, float inv_div) {
   constexpr int DH = 64, S = 256;
   using L = AttnBwd2Smem;
   extern __shared__ uint8_t smem_raw[];
@@ -950,15 +950,36 @@ attn_bwd_s256_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 #pragma unroll 1
       for (int p = 0; p < 3; ++p, ++t) {
         const int i = p == 0 ? 0 : 1, j = p == 2 ? 1 : 0;
-        if (p < 2) {   // first pair of query tile i: its row statistics
+        uint4 ov[8], gv[8];
+        if (p < 2) {   // first pair of query tile i: its row statistics; D = sum_d dO * O of the row is computed here
+          // (the split kernels take it from attn_bwd_prep_kernel: one launch per layer less).  The 2 x 128 bytes are
+          // requested before the waits below and used after them.
           const int64_t stat = ((int64_t)b * h + hh) * S + i * 128 + row;
           lse_r = lse[stat];
-          D_r = D[stat];
+          const int64_t q_glob = (int64_t)b * S + i * 128 + row;
+          const uint4* po = reinterpret_cast<const uint4*>(o_fwd + (q_glob * h + hh) * DH);
+          const uint4* pg = reinterpret_cast<const uint4*>(d_o + (q_glob * h + hh) * DH);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { ov[k] = __ldg(po + k); gv[k] = __ldg(pg + k); }
         }
         if (pend_p >= 0) {   // previous step: its accumulate MMAs retired -> P / dS tiles are free, its outputs complete
           mbar_wait(acc_done, (t - 1) & 1);
           fence_after();
           read_out();
+        }
+        if (p < 2) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&ov[k]);
+            const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&gv[k]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 x = __bfloat1622float2(pa[u]), y = __bfloat1622float2(pb[u]);
+              acc += x.x * y.x + x.y * y.y;
+            }
+          }
+          D_r = acc;
         }
         mbar_wait(s_full, t & 1);
         fence_after();
@@ -1025,21 +1046,10 @@ static int attention_bwd_t(const void* qkv_bf16, const void* out_bf16, const voi
                            int B, int S, int h, float divisor, float* D, cudaStream_t st) {
   using C = AttnCfg<DH>;
   const int64_t rows = (int64_t)B * S * h;
-  NPT_CHECK_CUDA(launch_pdl(attn_bwd_prep_kernel<DH>, dim3((unsigned)cdiv(rows * 8, 256)), dim3(256), 0, st,
-                            (const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)d_out_bf16, D, rows, S, h));
-  NPT_LAUNCH_CHECK();
   CUtensorMap tmQKV, tmDO;
   const int sw = C::CH == 64 ? 128 : 64;
   if (int rc = make_map_bf16_2d(&tmQKV, qkv_bf16, (int64_t)h * 3 * DH, (int64_t)B * S, (int64_t)h * 3 * DH, C::CH, 128, sw)) return rc;
   if (int rc = make_map_bf16_2d(&tmDO, d_out_bf16, (int64_t)h * DH, (int64_t)B * S, (int64_t)h * DH, C::CH, 128, sw)) return rc;
-  auto kdkv = attn_bwd_dkv_kernel<DH>;
-  auto kdq = attn_bwd_dq_kernel<DH>;
-  static bool attr = false;
-  if (!attr) {
-    NPT_CHECK_CUDA(cudaFuncSetAttribute(kdkv, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDkvSmem<DH>::TOTAL));
-    NPT_CHECK_CUDA(cudaFuncSetAttribute(kdq, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem<DH>::TOTAL));
-    attr = true;
-  }
   const float inv_div = 1.0f / divisor;
   if (DH == 64 && S == 256 && !attn_bwd_force_split()) {   // both tiles of a sequence in one CTA: dQ, dK, dV in one pass
     static bool attr2 = false;
@@ -1048,9 +1058,21 @@ static int attention_bwd_t(const void* qkv_bf16, const void* out_bf16, const voi
       attr2 = true;
     }
     NPT_CHECK_CUDA(launch_pdl(attn_bwd_s256_kernel, dim3(persistent_grid(B * h)), dim3(AT_THREADS), AttnBwd2Smem::TOTAL, st, tmQKV,
-                              tmDO, lse, (const float*)D, (__nv_bfloat16*)dqkv_bf16, B, h, inv_div));
+                              tmDO, lse, (const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)d_out_bf16, (__nv_bfloat16*)dqkv_bf16,
+                              B, h, inv_div));
     NPT_LAUNCH_CHECK();
     return 0;
+  }
+  NPT_CHECK_CUDA(launch_pdl(attn_bwd_prep_kernel<DH>, dim3((unsigned)cdiv(rows * 8, 256)), dim3(256), 0, st,
+                            (const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)d_out_bf16, D, rows, S, h));
+  NPT_LAUNCH_CHECK();
+  auto kdkv = attn_bwd_dkv_kernel<DH>;
+  auto kdq = attn_bwd_dq_kernel<DH>;
+  static bool attr = false;
+  if (!attr) {
+    NPT_CHECK_CUDA(cudaFuncSetAttribute(kdkv, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDkvSmem<DH>::TOTAL));
+    NPT_CHECK_CUDA(cudaFuncSetAttribute(kdq, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem<DH>::TOTAL));
+    attr = true;
   }
   const int grid = persistent_grid(B * h * (S / 128));
   NPT_CHECK_CUDA(launch_pdl(kdkv, dim3(grid), dim3(AT_THREADS), AttnDkvSmem<DH>::TOTAL, st, tmQKV, tmDO, lse, (const float*)D,
