@@ -61,6 +61,14 @@ def main(tp, dp):
         np.testing.assert_array_equal(p.data.numpy(), want, err_msg=name)
     lo, hi = O.vocab_chunk_bounds(17, tp, tr)
     assert (npdist.get_var("embedding_chunk_start"), npdist.get_var("embedding_chunk_end")) == (lo, hi)
+    if tp > 1:
+        # bookkeeping of the small-vocabulary gather path (InputEmbedding.gathers_full_table): every rank knows every
+        # rank's chunk bounds and shard width; 17 % 2 == 1, so the reference's bounds coincide with the shards
+        emb = model.input_embedding
+        assert emb._chunks == [O.vocab_chunk_bounds(17, tp, r)[0] for r in range(tp)] + [O.vocab_chunk_bounds(17, tp, tp - 1)[1]]
+        assert emb._widths == [O.shard(full["embedding"], tp, r, 1).shape[1] for r in range(tp)]
+        assert sum(emb._widths) == 17 and emb._chunks[tr + 1] - emb._chunks[tr] == emb.embedding.data.shape[1]
+        assert emb.gathers_full_table(10_000) is False   # no CUDA device here: the path is GPU-only
     assert model.block_0.mlp.row_linear.use_bias == (tr == 0)                      # Q17
     assert model.is_scattered and model.block_1.attention.is_scattered
     m = opt.parameters["block_0"]["mlp"]["column_linear"]["weight"].momentum.data
