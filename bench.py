@@ -520,6 +520,7 @@ def run_ours(args):
 
     # ---- roofline legs: every launch of one eager step, CUDA events on the launching stream ---------------
     roof, hbm, att = profile_eager_step(step, model, opt, main["dev_batches"][0], main["ms_per_step"], args.precision)
+    barrier()   # tp = 2: the replayed GEMMs push tiles into the peer's memory — nobody moves on (or tears down) before both are done
     roof["traffic"], roof["traffic_source"] = gemm_traffic(args.config, args.precision, n_gpus)
 
     # ---- fp32-accurate mode (the reference's own precision), a few steps, c1 / N = 1 only -------------------
