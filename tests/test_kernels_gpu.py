@@ -609,3 +609,107 @@ def test_errors_are_reported_not_swallowed():
         ops.gemm(a, a, 128, 64, 64, lda=64, ldb=64, C_out=rt.empty((128, 64)), ldc=64, mode=0)  # bf16 into the fp32 kernel
     with pytest.raises(NptError, match="head_dim 64 and 96"):
         ops.attention_fwd(rt.empty((1, 128, 3 * 80), torch.bfloat16), 1, 128, 1, 80, 10.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor parallelism over two ranks, kernel level, on ONE GPU: the "peer" buffers are local tensors.
+# (The two-GPU end-to-end parity is tests/test_multigpu.py; these run wherever a single B200 is available.)
+# ---------------------------------------------------------------------------------------------
+def test_gemm_split_peer_store():
+    """npt_gemm_args.peer_rows_lo/hi: tiles of the rows in [lo, hi) go to C_bf16_peer ONLY, the others to C_bf16 only
+    (the reduce-scatter by push of distributed/peer.py); without the bounds every tile goes to both."""
+    rng = np.random.default_rng(7)
+    M, N, K = 512, 384, 192
+    a, b = bf16_round(rng.standard_normal((M, K))), bf16_round(rng.standard_normal((K, N)))
+    want = a.astype(np.float64) @ b.astype(np.float64)
+    at, bt = dev(a).bfloat16(), dev(b).bfloat16()
+    own = torch.full((M, N), 7.0, dtype=torch.bfloat16, device="cuda")
+    peer = torch.full((M, N), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(at, bt, M, N, K, lda=K, ldb=N, Cb_out=own, ldcb=N, Cb_peer=(peer.data_ptr(), 256, 512), mode=1)
+    o, p = host(own), host(peer)
+    close(o[:256], want[:256], 1e-2)
+    close(p[256:], want[256:], 1e-2)
+    assert (o[256:] == 7.0).all() and (p[:256] == 7.0).all()          # untouched halves
+    ops.gemm(at, bt, M, N, K, lda=K, ldb=N, Cb_out=own, ldcb=N, Cb_peer=peer.data_ptr(), mode=1)
+    np.testing.assert_array_equal(host(own), host(peer))               # double store
+    close(host(own), want, 1e-2)
+
+
+class _FakeExchange:
+    """Stands in for distributed.peer.PeerExchange on one GPU: `bufs[r]` plays rank r's arena."""
+
+    def __init__(self, rank, pools):
+        self.rank, self.pools, self.i = rank, pools, 0
+
+    def arena(self, shape, dtype):
+        key = self.i
+        self.i += 1
+        for r in (0, 1):
+            if key not in self.pools[r]:
+                self.pools[r][key] = torch.zeros(shape, dtype=dtype, device="cuda")
+        return self.pools[self.rank][key], self.pools[1 - self.rank][key].data_ptr()
+
+
+@pytest.mark.parametrize("T,d", [(256, 384), (512, 768), (256, 1024)])
+def test_layernorm_row_sharded_two_ranks_on_one_gpu(T, d):
+    """npt_layernorm_fwd_v3 / _bwd_v4 as distributed/peer.py drives them: two ranks hold partial sums x0 + x1 of the
+    LayerNorm input (and dy0 + dy1 of its output gradient); rank r normalises rows [r T/2, (r+1) T/2) and pushes
+    its bf16 results and per-block gradient partials into the other rank's buffers.  Afterwards both ranks must hold
+    the complete tensors, equal to the LayerNorm of round_bf16(x0 + x1) (nn/normalization.py:22-52 after the
+    reference's all-reduce, nn/attention.py:57-58)."""
+    rng = np.random.default_rng(T + d)
+    x0 = bf16_round(0.75 + 0.02 * rng.standard_normal((1, T, d)))
+    x1 = bf16_round(0.75 + 0.02 * rng.standard_normal((1, T, d)))
+    dy0, dy1 = bf16_round(rng.standard_normal((1, T, d))), bf16_round(rng.standard_normal((1, T, d)))
+    g = rng.random(d).astype(np.float32) * 0.2
+    b = (rng.standard_normal(d) * 0.1).astype(np.float32)
+    res = rng.standard_normal((1, T, d)).astype(np.float32)
+    x, dy = bf16_round(x0 + x1), bf16_round(dy0 + dy1)
+    y_ref, ctx = O.layernorm_forward(x, g, b)
+    dx_ref, dg_ref, db_ref = O.layernorm_backward(ctx, g, dy)
+    H = T // 2
+    xs, dys = [dev(x0).bfloat16(), dev(x1).bfloat16()], [dev(dy0).bfloat16(), dev(dy1).bfloat16()]
+    gt, bt, rt_ = dev(g), dev(b), dev(res)
+    pools = ({}, {})
+    state = []
+    for r in (0, 1):       # forward of both ranks (rank r: own partial xs[r], received partial xs[1 - r])
+        px = _FakeExchange(r, pools)
+        y, mean, var, x_sum = ops.layernorm_fwd_rows(xs[r], xs[1 - r].data_ptr(), gt, bt, 1e-5, rt_, (r * H, H), px)
+        state.append((px, y, mean, var, x_sum))
+    for r in (0, 1):
+        px, y, mean, var, x_sum = state[r]
+        rows = slice(r * H, (r + 1) * H)
+        close(host(y)[0, rows], (y_ref + res)[0, rows], 2e-5)                       # fp32 result: own rows
+        close(host(x_sum)[0, rows], x[0, rows], 1e-6)
+        close(host(y._npt_bf16)[0], (y_ref + res)[0], 1e-2)                         # bf16 result: EVERY row, on both ranks
+    np.testing.assert_array_equal(host(state[0][1]._npt_bf16), host(state[1][1]._npt_bf16))
+    finishes = []
+    for r in (0, 1):       # backward of both ranks
+        px, y, mean, var, x_sum = state[r]
+        dx, finish = ops.layernorm_bwd_rows(x_sum, gt, mean, var, dys[r], dys[1 - r].data_ptr(), 1e-5, (r * H, H), px, True)
+        finishes.append((dx, finish))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(host(finishes[0][0]), host(finishes[1][0]))        # dx complete and identical on both
+    close(host(finishes[0][0]), dx_ref, 1e-2)
+    grads = [f() for _, f in finishes]
+    for k, want in enumerate((dg_ref, db_ref, dx_ref.reshape(T, d).astype(np.float64).sum(0))):
+        np.testing.assert_array_equal(host(grads[0][k]), host(grads[1][k]))          # replicated parameters stay bit-identical
+        close(host(grads[0][k]), want, 2e-2 if k == 2 else 1e-3)
+    with rt.deferred_wgrad():   # inside the graphed step the two stacks go to Adam un-reduced: same sums
+        stacks = finishes[0][1]()
+    for k in range(3):
+        assert stacks[k]._npt_splits == stacks[k].shape[0] and stacks[k]._npt_split_stride == 3 * d
+        close(host(stacks[k]).astype(np.float64).sum(0), host(grads[0][k]), 1e-5)
+
+
+def test_memcpy2d_reassembles_vocabulary_shards():
+    """npt_memcpy2d_async: the (d, V) embedding table put back together from two pitched shards (nn/embedding.py:19-37)."""
+    lib = __import__("numpitron_b200._lib", fromlist=["load"]).load()
+    rng = np.random.default_rng(11)
+    d, w0, w1 = 48, 33, 32
+    E = rng.standard_normal((d, w0 + w1)).astype(np.float32)
+    shards = [dev(np.ascontiguousarray(E[:, :w0])), dev(np.ascontiguousarray(E[:, w0:]))]
+    full = rt.zeros((d, w0 + w1))
+    for sh, off, w in ((shards[0], 0, w0), (shards[1], w0, w1)):
+        ops.check(lib.npt_memcpy2d_async(full.data_ptr() + off * 4, (w0 + w1) * 4, sh.data_ptr(), w * 4, w * 4, d, rt.stream()), "memcpy2d")
+    np.testing.assert_array_equal(host(full), E)
