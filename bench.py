@@ -109,8 +109,13 @@ def run_reference_world(config: str, n_ranks: int, steps: int, warmup: int, budg
         for r in range(n_ranks):
             env = dict(os.environ, WORLD_SIZE=str(n_ranks), RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
                        OPENBLAS_NUM_THREADS=str(threads), OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads))
-            for k in ("LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "TORCHELASTIC_RUN_ID"):
-                env.pop(k, None)
+            # under torchrun the parent's environment describes ITS world: drop all of it — in particular
+            # TORCHELASTIC_USE_AGENT_STORE, which would make rank 0 of this CPU world wait for the elastic agent's
+            # store on the new port instead of starting its own (every rank then hangs in the rendezvous)
+            for k in list(env):
+                if k.startswith("TORCHELASTIC_") or k in ("LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE",
+                                                          "ROLE_RANK", "ROLE_WORLD_SIZE", "ROLE_NAME", "TORCH_NCCL_ASYNC_ERROR_HANDLING"):
+                    env.pop(k, None)
             procs.append(subprocess.Popen([sys.executable, str(ROOT / "baseline" / "reference_worker.py"), json.dumps(spec)],
                                           env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
         results, deadline = [], time.time() + budget_s * 3 + 300
