@@ -25,6 +25,10 @@ struct Group {
 // tail.  f(v, x) is called for every element (v = column).
 template <typename F>
 __device__ __forceinline__ void ce_row_read(const float* __restrict__ lr, int V, int tid, int n, F f) {
+  if (V < 128) {   // a row of the Shakespeare vocabulary is 65 floats: 32 lanes x scalar loads beat 15 lanes x float4
+    for (int v = tid; v < V; v += n) f(v, lr[v]);
+    return;
+  }
   int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(lr) & 15u)) & 15u) >> 2);
   if (head > V) head = V;
   for (int v = tid; v < head; v += n) f(v, lr[v]);
@@ -102,7 +106,7 @@ ce_kernel(const float* __restrict__ logits, int64_t ld, const uint16_t* __restri
     if (inside && v == label) p = __fsub_rn(p, 1.0f);
     return p;
   };
-  if ((reinterpret_cast<uintptr_t>(gr) & 15u) == (reinterpret_cast<uintptr_t>(lr) & 15u)) {
+  if (V >= 128 && (reinterpret_cast<uintptr_t>(gr) & 15u) == (reinterpret_cast<uintptr_t>(lr) & 15u)) {
     // the gradient row has the alignment of the logits row (same pitch): 128-bit loads and stores
     int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(lr) & 15u)) & 15u) >> 2);
     if (head > V) head = V;
