@@ -111,7 +111,18 @@ sa_colscan_kernel(int* __restrict__ table, int* __restrict__ counts, int nchunks
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
   int run = 0;
-  for (int c = 0; c < nchunks; ++c) {
+  int c = 0;
+  for (; c + 16 <= nchunks; c += 16) {   // sixteen independent loads, then the running sum (the loop was one load per step)
+    int n[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) n[u] = table[(size_t)(c + u) * V + v];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      table[(size_t)(c + u) * V + v] = run;
+      run += n[u];
+    }
+  }
+  for (; c < nchunks; ++c) {
     const int n = table[(size_t)c * V + v];
     table[(size_t)c * V + v] = run;
     run += n;
@@ -161,7 +172,7 @@ sa_fill_kernel(const uint16_t* __restrict__ tokens, const int* __restrict__ tabl
   order[offsets[v] + table[(size_t)c * V + v] + rank[t]] = (int)t;
 }
 
-// grid (V, ceil(d/128)); sequential fp32 adds in segment order, 8 loads in flight per thread.
+// grid (V, ceil(d/128)); sequential fp32 adds in segment order, 16 loads in flight per thread.
 __global__ void __launch_bounds__(128)
 sa_accumulate_kernel(const int* __restrict__ offsets, const int* __restrict__ order,
                      const float* __restrict__ d_out, float* __restrict__ grad, int64_t ldG, int d) {
@@ -173,15 +184,25 @@ sa_accumulate_kernel(const int* __restrict__ offsets, const int* __restrict__ or
   if (beg == end || c >= d) return;
   float acc = grad[(int64_t)c * ldG + v];
   int i = beg;
-  for (; i + 8 <= end; i += 8) {
-    int idx[8];
-    float a[8];
+  for (; i + 16 <= end; i += 16) {   // sixteen loads in flight per thread: the chain of additions is latency-bound
+    int idx[16];
+    float a[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) idx[u] = __ldg(order + i + u);
+    for (int u = 0; u < 16; ++u) idx[u] = __ldg(order + i + u);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) a[u] = __ldg(d_out + (int64_t)idx[u] * d + c);
+    for (int u = 0; u < 16; ++u) a[u] = __ldg(d_out + (int64_t)idx[u] * d + c);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, a[u]);  // strictly in order
+    for (int u = 0; u < 16; ++u) acc = __fadd_rn(acc, a[u]);  // strictly in order
+  }
+  for (; i + 4 <= end; i += 4) {
+    int idx[4];
+    float a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) idx[u] = __ldg(order + i + u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = __ldg(d_out + (int64_t)idx[u] * d + c);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc = __fadd_rn(acc, a[u]);
   }
   for (; i < end; ++i) acc = __fadd_rn(acc, __ldg(d_out + (int64_t)__ldg(order + i) * d + c));
   grad[(int64_t)c * ldG + v] = acc;
