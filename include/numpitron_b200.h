@@ -216,12 +216,13 @@ int npt_softmax_causal_bwd(const void* p, int32_t p_is_bf16, const float* dp, fl
                            int64_t n_mats, int32_t S, float divisor, void* stream);
 
 /* ---- fused causal attention (bf16 mode; P never leaves the SM) --------------------------------------
- * Replaces nn/attention.py:43-52 (forward) and :81-98 (backward) for head_dim 64 and S % 128 == 0;
- * other shapes use npt_gemm + npt_softmax_causal_*.  qkv is the QKV projection output
+ * Replaces nn/attention.py:43-52 (forward) and :81-98 (backward) for head_dim 64 or 96 (96 = the single local head of
+ * GPT-2 small under tp = 8, attention.py:37-45) and S % 128 == 0; other shapes use npt_gemm + npt_softmax_causal_*.  qkv is the QKV projection output
  * (B,S,h,3,Dh) bf16 exactly as attention.py:43-45 lays it out ([q_h|k_h|v_h] per head); `out` /
  * `d_out` are the merged heads (B,S,h*Dh) bf16; lse is the per-row log-sum-exp (B,h,S) fp32 saved
  * for the backward; dqkv (B,S,h,3,Dh) bf16 = concat([dq,dk,dv],-1) merged back (attention.py:94-98).
- * divisor = sqrt(d_model) (attention.py:48).  Deterministic (no atomics).
+ * divisor = sqrt(d_model) (attention.py:48).  Deterministic (no atomics).  The workspace of the backward holds
+ * D = sum_d dO * O per row; for S = 256, head_dim 64 one kernel computes dQ, dK and dV (and D) in a single pass.
  */
 int npt_attention_supported(int32_t S, int32_t Dh);
 int npt_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int32_t B, int32_t S, int32_t h,
