@@ -124,7 +124,7 @@ def enabled() -> bool:
     from . import tensor_parallel_size
 
     return (not _state["failed"] and os.environ.get("NUMPITRON_TP_PEER", "1") != "0" and rt.is_bf16()
-            and tensor_parallel_size() == 2 and torch.cuda.is_available())
+            and not rt.ln_inputs_fp32() and tensor_parallel_size() == 2 and torch.cuda.is_available())
 
 
 def exchange(shape, dtype=torch.bfloat16):

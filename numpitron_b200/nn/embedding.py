@@ -130,7 +130,7 @@ class OutputEmbedding(Layer):
         # d @ E^T.  In bf16 mode this dX is read by the last block's LayerNorm backward, which takes bf16
         # (the value it would otherwise be cast to): let the GEMM epilogue write bf16 directly.
         d_model = self.input_embedding.embedding.data.shape[0]
-        out = "bf16" if rt.is_bf16() and ops.layernorm_bf16_input_supported(d_model) else "f32"
+        out = "bf16" if rt.is_bf16() and ops.layernorm_bf16_input_supported(d_model) and not rt.ln_inputs_fp32() else "f32"
         tp = self.is_scattered and npdist.tensor_parallel_size() > 1
         if tp and out == "bf16" and peer.enabled():
             # tp = 2: no all-reduce kernel — the partial goes to the other rank's memory from the GEMM epilogue and

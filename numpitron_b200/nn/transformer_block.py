@@ -27,7 +27,7 @@ class TransformerBlock(Model):
         """bf16 mode: the sub-layer outputs LayerNorm normalises, and the dX that reaches a LayerNorm's
         backward, leave their GEMM as bf16 alone (the residual stream itself stays fp32): half the bytes to
         store, to all-reduce across tensor-parallel ranks and for LayerNorm to read."""
-        if not (rt.is_bf16() and ops.layernorm_bf16_input_supported(self.d_model)):
+        if not (rt.is_bf16() and ops.layernorm_bf16_input_supported(self.d_model)) or rt.ln_inputs_fp32():
             return "f32"
         # tp = 2: the partial results are exchanged through peer memory and reduced inside LayerNorm
         return "peer" if peer.enabled() else "bf16"

@@ -39,6 +39,15 @@ def is_bf16() -> bool:
     return _state["precision"] == BF16
 
 
+def ln_inputs_fp32() -> bool:
+    """NUMPITRON_LN_INPUT=fp32 (bf16 mode, an accuracy / speed A-B knob): the two tensors per sub-layer that sit between
+    a GEMM and a LayerNorm — the sub-layer output it normalises and the dX that reaches its backward — stay fp32
+    instead of leaving the GEMM epilogue as bf16.  Their rows ride on a mean 30-70x their std, so bf16
+    storage costs ~10 % of the normalised value per element; fp32 storage costs 12.6 MB more to write and to read
+    per tensor at the bench shape.  Off by default; not available with the tp = 2 peer exchange (which moves bf16)."""
+    return os.environ.get("NUMPITRON_LN_INPUT", "bf16") == "fp32"
+
+
 # ---- device ---------------------------------------------------------------------------------
 def device() -> torch.device:
     """cuda:<LOCAL_RANK> when a GPU is present, else cpu (host-side setup/tests only)."""
